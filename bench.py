@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native csnappy hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--pages P]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1], "zram-style batch"): per GPU 1 Mi synthetic 4 KiB pages
+(50 % word text, 25 % zero, 25 % random; csnappy_b200/synth.py), csnappy_compress_fragment
+semantics with workmem_bytes_power_of_two = 13, then csnappy_decompress_noheader of the result.
+One STEP = compress the whole batch + decompress the whole batch.  Metric: GB/s of UNCOMPRESSED
+bytes through the codec = (bytes compressed + bytes decompressed) / step time, whole job
+(sum over ranks, max time over ranks).  Pages are independent, so ranks shard the page range
+with no data-path collective ("weak": per-GPU batch fixed); NCCL is used for the barrier and
+the max-over-ranks only.
+
+`value`      device-resident: inputs already in HBM, CUDA events around K steps.
+`e2e`        same metric through the host-buffer C-ABI (csnappy_batch_*_host) with pinned
+             host buffers: H2D of every page and D2H of every result inside the timed region.
+`roofline`   dominant kernel (compress) against the measured HBM copy peak;
+             algorithmic bytes = sum N_in + sum C_out + 4 B.
+`cpu_baseline` the unmodified reference (oracle/_ref) or the oracle port on this box's cores.
+--impl reference times that CPU implementation alone, on a bounded sample per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+PAGE = 4096
+WM = 13
+SEED = 0x5EED0001
+METRIC = "compress+decompress throughput, GB/s of uncompressed data, 4 KiB pages (wm 13)"
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-i", str(self.idx), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, reasons, mx = [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx = float(c[2])
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def cpu_codec_pass(host_pages, threads: int, impl: str, repeats: int = 3):
+    """compress + decompress `host_pages` [S, PAGE] on the CPU.  -> (best_comp_s, best_dec_s, out, lens)"""
+    import numpy as np
+
+    import oracle
+
+    best_c = best_d = float("inf")
+    out = lens = None
+    for _ in range(repeats):
+        out, lens, sc = oracle.batch_compress(host_pages, WM, impl, threads=threads)
+        best_c = min(best_c, sc)
+    for _ in range(repeats):
+        back, blen, st, sd = oracle.batch_decompress(out, lens, PAGE, impl, threads=threads)
+        best_d = min(best_d, sd)
+    assert (st == 0).all() and (blen == PAGE).all() and (back[:, :PAGE] == host_pages).all()
+    return best_c, best_d, out, lens
+
+
+def run_reference(args, rank: int, world: int):
+    """--impl reference: the reference's own CPU implementation on this box's cores."""
+    if rank != 0:
+        return
+    import numpy as np
+    import torch
+
+    import oracle
+    from csnappy_b200 import synth
+
+    impl = "reference" if oracle.have_reference() else "port"
+    cores = host_cores()
+    S = min(args.pages, 1 << 16)  # bounded sample per step: 64 Ki pages = 256 MiB
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    pages = synth.mixed_pages(S, PAGE, seed=SEED, device=dev).view(S, PAGE).cpu().numpy()
+    times = []
+    for it in range(args.warmup + args.steps):
+        tc, td, _, _ = cpu_codec_pass(pages, cores, impl, repeats=1)
+        if it >= args.warmup:
+            times.append(tc + td)
+    total = sum(times)
+    value = 2 * S * PAGE * args.steps / total / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": "GB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * total / args.steps, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "zram-style batch: synthetic 4 KiB pages (50% text / 25% zero / 25% random), wm 13, "
+                               "compress then decompress", "pages_per_gpu": args.pages, "page_bytes": PAGE, "wm": WM},
+        "cpu_baseline": {"value": round(value, 3), "unit": "GB/s", "cores": cores, "kind": impl,
+                         "sample": f"{S} pages ({S * PAGE >> 20} MiB) per step, compress + decompress, "
+                                   f"{cores} pthreads, static partition"},
+        "e2e": {"value": round(value, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pages", type=int, default=1 << 20, help="pages per GPU (default 1 Mi = 4 GiB)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--lanes-c", type=int, default=0)
+    ap.add_argument("--lanes-d", type=int, default=0)
+    ap.add_argument("--ctas-per-sm", type=int, default=0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import csnappy_b200 as cs
+    from csnappy_b200 import shard, synth
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert cs.device_ok(), cs.api.last_error()
+    if args.lanes_c:
+        cs.set_tuning("compress_lanes", args.lanes_c)
+    if args.lanes_d:
+        cs.set_tuning("decompress_lanes", args.lanes_d)
+    if args.ctas_per_sm:
+        cs.set_tuning("ctas_per_sm", args.ctas_per_sm)
+
+    B = args.pages
+    first, _ = shard.block_range(B * world, rank, world)  # weak scaling: rank r owns pages [r*B, (r+1)*B)
+    pages = synth.mixed_pages(B, PAGE, seed=SEED, device=dev, first_page=first)
+    ostride = cs.api.out_stride_for(PAGE)
+    comp = torch.empty(B * ostride, dtype=torch.uint8, device=dev)
+    comp_len = torch.empty(B, dtype=torch.int32, device=dev)
+    back = torch.empty(B * PAGE, dtype=torch.uint8, device=dev)
+    back_len = torch.empty(B, dtype=torch.int32, device=dev)
+    status = torch.empty(B, dtype=torch.int32, device=dev)
+
+    def step(ev=None):
+        if ev:
+            ev[0].record()
+        cs.batch_compress_fragments(pages, PAGE, B, WM, out=comp, out_len=comp_len, out_stride=ostride)
+        if ev:
+            ev[1].record()
+        cs.batch_decompress(comp, comp_len, B, PAGE, in_stride=ostride, out=back, out_stride=PAGE,
+                            out_len=back_len, status=status)
+        if ev:
+            ev[2].record()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    # correctness of what is being timed: exact round trip + all-OK status
+    assert int((status != 0).sum()) == 0 and int((back_len != PAGE).sum()) == 0
+    assert torch.equal(back, pages), "round trip mismatch"
+    csum = int(comp_len.sum())
+
+    sampler = ClockSampler(local_rank)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = cs.kernel_launches()
+    barrier()
+    if rank == 0:
+        sampler.start()
+    t0.record()
+    for k in range(args.steps):
+        step(evs[k])
+    t1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = cs.kernel_launches() - launches0
+    elapsed_ms = t0.elapsed_time(t1)
+    tc_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in evs)
+    td_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in evs)
+
+    # ---- e2e through the host-buffer C-ABI with pinned host memory ------------------------
+    e2e_ms = None
+    h2d = d2h = 0
+    if not args.no_e2e:
+        h_in = torch.empty(B * PAGE, dtype=torch.uint8, pin_memory=True)
+        h_comp = torch.empty(B * ostride, dtype=torch.uint8, pin_memory=True)
+        h_len = torch.empty(B, dtype=torch.int32, pin_memory=True)
+        h_back = torch.empty(B * PAGE, dtype=torch.uint8, pin_memory=True)
+        h_blen = torch.empty(B, dtype=torch.int32, pin_memory=True)
+        h_st = torch.empty(B, dtype=torch.int32, pin_memory=True)
+        h_in.copy_(pages)
+        torch.cuda.synchronize()
+
+        def e2e_step():
+            cs.batch_compress_fragments_host(h_in, PAGE, B, WM, h_comp, h_len)
+            cs.batch_decompress_host(h_comp, ostride, h_len, B, h_back, PAGE, PAGE, h_blen, h_st)
+
+        e2e_step()
+        assert int((h_st != 0).sum()) == 0 and torch.equal(h_back, h_in)
+        n_e2e = max(2, min(args.steps, 5))
+        barrier()
+        w0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        torch.cuda.synchronize()
+        e2e_ms = 1e3 * (time.perf_counter() - w0) / n_e2e
+        h2d = B * PAGE + B * ostride + B * 4
+        d2h = B * ostride + B * 4 + B * PAGE + B * 8
+        del h_in, h_comp, h_back
+
+    # ---- reduce over ranks: max time, sum bytes -------------------------------------------
+    vals = torch.tensor([elapsed_ms, tc_ms, td_ms, e2e_ms or 0.0], dtype=torch.float64, device=dev)
+    sums = torch.tensor([float(B * PAGE), float(csum), float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    elapsed_ms, tc_ms, td_ms, e2e_max = vals.tolist()
+    total_n, total_c, total_launches = sums.tolist()
+
+    if rank == 0:
+        ms_per_step = elapsed_ms / args.steps
+        value = 2 * total_n / (ms_per_step * 1e-3) / 1e9
+        peak, peak_src = measured_peak()
+        # roofline of the dominant kernel, per launch on ONE GPU (rank 0's kernel times are the max over ranks)
+        alg_c = B * PAGE + total_c / world + 4 * B
+        alg_d = total_c / world + B * PAGE + 8 * B
+        ach_c = alg_c / (tc_ms * 1e-3) / 1e9
+        ach_d = alg_d / (td_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f)
+        dominant = "compress" if tc_ms >= td_ms else "decompress"
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "zram-style batch: synthetic 4 KiB pages (50% text / 25% zero / 25% random), "
+                                   "wm 13, compress then decompress", "pages_per_gpu": B, "page_bytes": PAGE,
+                       "wm": WM, "ratio": round(total_c / total_n, 4), "parallelism": f"shard{world} (no collective)",
+                       "l2": "inputs (4 GiB per GPU) exceed the 126 MB L2; no explicit flush",
+                       "value_definition": "(bytes compressed + bytes decompressed) / step time"},
+            "compress_gbs": round(total_n / (tc_ms * 1e-3) / 1e9, 2),
+            "decompress_gbs": round(total_n / (td_ms * 1e-3) / 1e9, 2),
+            "roofline": {"kernel": f"{dominant}_kernel", "bound": "hbm",
+                         "achieved": round(ach_c if dominant == "compress" else ach_d, 2), "peak": peak,
+                         "unit": "GB/s", "frac": round((ach_c if dominant == "compress" else ach_d) / peak, 4),
+                         "traffic": (traffic or {}).get(dominant), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": int(alg_c if dominant == "compress" else alg_d),
+                         "kernel_ms": round(tc_ms if dominant == "compress" else td_ms, 3)},
+            "roofline_other": {"kernel": ("decompress" if dominant == "compress" else "compress") + "_kernel",
+                               "achieved": round(ach_d if dominant == "compress" else ach_c, 2),
+                               "frac": round((ach_d if dominant == "compress" else ach_c) / peak, 4),
+                               "kernel_ms": round(td_ms if dominant == "compress" else tc_ms, 3)},
+            "gpu_launches": int(total_launches),
+            "clocks": clocks,
+        }
+        if e2e_max:
+            line["e2e"] = {"value": round(2 * total_n / (e2e_max * 1e-3) / 1e9, 2), "unit": "GB/s",
+                           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                           "ms_per_step": round(e2e_max, 2),
+                           "api": "csnappy_batch_compress_fragments_host + csnappy_batch_decompress_host, pinned host buffers"}
+        if world == 1 and not args.no_cpu:
+            import oracle
+
+            impl = "reference" if oracle.have_reference() else "port"
+            cores = host_cores()
+            S = min(B, 1 << 18)
+            host = pages.view(B, PAGE)[:S].cpu().numpy()
+            tc, td, ref_out, ref_len = cpu_codec_pass(host, cores, impl)
+            t1c, _, _, _ = cpu_codec_pass(host[: S // 8], 1, impl, repeats=1)
+            # the same pass is the bulk parity check of what was timed
+            got_len = comp_len[:S].cpu().numpy().astype(np.uint32)
+            assert (got_len == ref_len).all(), "GPU compressed sizes differ from the CPU reference"
+            line["cpu_baseline"] = {
+                "value": round(2 * S * PAGE / (tc + td) / 1e9, 3), "unit": "GB/s", "cores": cores, "kind": impl,
+                "sample": f"first {S} pages ({S * PAGE >> 20} MiB) of the same batch, compress + decompress, "
+                          f"best of 3, {cores} pthreads",
+                "compress_gbs": round(S * PAGE / tc / 1e9, 3), "decompress_gbs": round(S * PAGE / td / 1e9, 3),
+                "single_thread_compress_gbs": round((S // 8) * PAGE / t1c / 1e9, 3)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,97 @@
+// device_common.cuh -- helpers shared by the sm_100a kernels.
+//
+// Execution model used by both codecs: a GROUP of G lanes (G = 8, 16 or 32, a
+// power-of-two slice of one warp) cooperates on one block; a CTA holds as many
+// groups as shared memory allows; the grid is persistent (a multiple of the SM
+// count) and groups claim blocks from a global counter.  All intra-group
+// communication is warp-level (ballot / shfl / match / syncwarp with the
+// group's lane mask), never __syncthreads, so groups progress independently.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace csb {
+
+constexpr uint32_t kHashMul = 0x1e35a7bdu;  // csnappy_compress.c:230
+
+template <int G>
+struct Group {
+	unsigned lane;    // 0..G-1 within the group
+	unsigned shift;   // first warp lane of the group
+	unsigned mask;    // warp lane mask of the group
+	__device__ __forceinline__ Group()
+	{
+		unsigned wl = threadIdx.x & 31u;
+		lane = wl & (G - 1);
+		shift = wl & ~(unsigned)(G - 1);
+		mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << shift);
+	}
+	__device__ __forceinline__ void sync() const { __syncwarp(mask); }
+	__device__ __forceinline__ unsigned ballot(bool p) const { return __ballot_sync(mask, p) >> shift; }
+	template <typename T>
+	__device__ __forceinline__ T bcast(T v, int src) const { return __shfl_sync(mask, v, src, G); }
+	__device__ __forceinline__ unsigned match(unsigned key) const { return __match_any_sync(mask, key) >> shift; }
+};
+
+// little-endian 32-bit load at an arbitrary byte offset of a 4-byte aligned shared-memory area
+__device__ __forceinline__ uint32_t lds32u(const uint8_t *area, uint32_t off)
+{
+	const uint32_t *w = reinterpret_cast<const uint32_t *>(area + (off & ~3u));
+	return __funnelshift_r(w[0], w[1], (off & 3u) * 8u);
+}
+
+__device__ __forceinline__ uint4 ldg_stream(const uint4 *p)
+{
+	uint4 r;
+	asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+		     : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+		     : "l"(p));
+	return r;
+}
+
+__device__ __forceinline__ void stg_stream(uint4 *p, const uint4 &v)
+{
+	asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y),
+		     "r"(v.z), "r"(v.w)
+		     : "memory");
+}
+
+// Cooperative copy of n bytes global -> shared (dst 16-byte aligned).  Vector path when src is
+// 16-byte aligned, 4-byte path when 4-aligned, byte path otherwise.  Never reads outside [src, src+n).
+template <int G>
+__device__ __forceinline__ void load_block_to_smem(const Group<G> &g, uint8_t *dst, const uint8_t *src, uint32_t n)
+{
+	const uintptr_t a = reinterpret_cast<uintptr_t>(src);
+	if ((a & 15u) == 0) {
+		const uint32_t nv = n >> 4;
+		const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+		uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+		for (uint32_t i = g.lane; i < nv; i += G)
+			d4[i] = ldg_stream(s4 + i);
+		for (uint32_t i = (nv << 4) + g.lane; i < n; i += G)
+			dst[i] = src[i];
+	} else if ((a & 3u) == 0) {
+		const uint32_t nw = n >> 2;
+		const uint32_t *s1 = reinterpret_cast<const uint32_t *>(src);
+		uint32_t *d1 = reinterpret_cast<uint32_t *>(dst);
+		for (uint32_t i = g.lane; i < nw; i += G)
+			d1[i] = __ldg(s1 + i);
+		for (uint32_t i = (nw << 2) + g.lane; i < n; i += G)
+			dst[i] = src[i];
+	} else {
+		for (uint32_t i = g.lane; i < n; i += G)
+			dst[i] = src[i];
+	}
+}
+
+struct DeviceInfo {
+	int sm_count;
+	int smem_per_block_optin;  // max dynamic shared memory per CTA (232448 on B200)
+	int smem_per_sm;	   // 233472 on B200
+};
+
+// cached per-device query; returns a cudaError_t
+int device_info(DeviceInfo *out);
+void count_launch();
+
+}  // namespace csb

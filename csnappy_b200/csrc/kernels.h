@@ -1,0 +1,63 @@
+/*
+ * kernels.h -- C-linkage launchers of the sm_100a kernels, called by the plain-C
+ * shim (csnappy_shim.c).  Internal to the library; the public ABI is include/*.h.
+ */
+#ifndef CSNAPPY_B200_KERNELS_H_
+#define CSNAPPY_B200_KERNELS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st *csb_stream_t; /* == cudaStream_t */
+
+#define CSB_FRAGMENT_MAX 32768u
+
+struct csb_compress_args {
+	const uint8_t *in;
+	const uint64_t *in_off; /* NULL => i * in_stride */
+	uint64_t in_stride;
+	const uint32_t *in_len; /* NULL => uniform_len (clipped by total_len if nonzero) */
+	uint32_t uniform_len;
+	uint64_t total_len;	/* nonzero: block i has min(uniform_len, total_len - i*in_stride) bytes */
+	uint32_t n_blocks;
+	uint8_t *out;
+	uint64_t out_stride;
+	uint32_t *out_len;
+	int wm;			/* log2 of hash-table bytes, 9..16 */
+	uint32_t flags;		/* CSNAPPY_BATCH_SHRINK_TABLE */
+	int lanes;		/* lanes cooperating on one block: 8, 16, 32 (0 = default) */
+	int ctas_per_sm;	/* 0 = default */
+};
+
+struct csb_decompress_args {
+	const uint8_t *in;
+	const uint64_t *in_off;
+	uint64_t in_stride;
+	const uint32_t *in_len;
+	uint32_t n_blocks;
+	uint8_t *out;
+	uint64_t out_stride;
+	const uint32_t *out_cap; /* NULL => uniform_cap */
+	uint32_t uniform_cap;
+	uint32_t *out_len;
+	int32_t *status;
+	uint32_t flags;		/* CSNAPPY_BATCH_WITH_HEADER */
+	uint32_t max_in_len;	/* staging hint: longest input block (0 = derive) */
+	int lanes;
+	int ctas_per_sm;
+};
+
+/* all return 0 or a cudaError_t value (> 0) */
+int csb_launch_compress(const struct csb_compress_args *a, csb_stream_t s);
+int csb_launch_decompress(const struct csb_decompress_args *a, csb_stream_t s);
+int csb_launch_pack(const uint8_t *slots, uint64_t slot_stride, const uint32_t *len,
+		    uint32_t n_blocks, uint8_t *packed, uint64_t *off, csb_stream_t s);
+uint64_t csb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,137 @@
+// pack_kernel.cu -- exclusive scan of per-block compressed sizes and gather of the strided
+// output slots into one contiguous payload.  Device-side equivalent of the running
+// `written += p - compressed` of csnappy_compress (/root/reference/csnappy_compress.c:647-653)
+// and of block_compressor's size index (block_compressor.c:298-335).  Also hosts the small
+// per-device bookkeeping shared by all launchers.
+#include <atomic>
+#include <mutex>
+
+#include "device_common.cuh"
+#include "kernels.h"
+
+namespace csb {
+
+static std::atomic<uint64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+int device_info(DeviceInfo *out)
+{
+	static std::mutex mu;
+	static DeviceInfo cache[64];
+	static bool have[64];
+	int dev = 0;
+	cudaError_t e = cudaGetDevice(&dev);
+	if (e != cudaSuccess)
+		return (int)e;
+	std::lock_guard<std::mutex> lk(mu);
+	if (dev < 0 || dev >= 64)
+		return (int)cudaErrorInvalidDevice;
+	if (!have[dev]) {
+		DeviceInfo di;
+		if ((e = cudaDeviceGetAttribute(&di.sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess)
+			return (int)e;
+		if ((e = cudaDeviceGetAttribute(&di.smem_per_block_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess)
+			return (int)e;
+		if ((e = cudaDeviceGetAttribute(&di.smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev)) != cudaSuccess)
+			return (int)e;
+		cache[dev] = di;
+		have[dev] = true;
+	}
+	*out = cache[dev];
+	return 0;
+}
+
+constexpr int kScanThreads = 1024;
+
+// single-CTA exclusive scan: off[i] = sum(len[0..i)), off[n] = total
+__global__ void __launch_bounds__(kScanThreads) scan_kernel(const uint32_t *__restrict__ len, uint32_t n,
+							    uint64_t *__restrict__ off)
+{
+	__shared__ uint64_t part[kScanThreads];
+	const uint32_t t = threadIdx.x;
+	const uint32_t per = (n + kScanThreads - 1) / kScanThreads;
+	const uint32_t lo = t * per < n ? t * per : n;
+	const uint32_t hi = lo + per < n ? lo + per : n;
+	uint64_t sum = 0;
+	for (uint32_t i = lo; i < hi; ++i)
+		sum += len[i];
+	part[t] = sum;
+	__syncthreads();
+	for (uint32_t d = 1; d < kScanThreads; d <<= 1) {  // Hillis-Steele inclusive scan
+		const uint64_t v = t >= d ? part[t - d] : 0;
+		__syncthreads();
+		part[t] += v;
+		__syncthreads();
+	}
+	uint64_t run = part[t] - sum;
+	for (uint32_t i = lo; i < hi; ++i) {
+		off[i] = run;
+		run += len[i];
+	}
+	if (t == kScanThreads - 1)
+		off[n] = part[t];
+}
+
+// one warp per block: packed[off[i] .. off[i]+len[i]) = slots[i*stride ..).  Destination words are
+// written 4-byte aligned; the (arbitrarily aligned) source is realigned with a funnel shift.
+__global__ void __launch_bounds__(256) gather_kernel(const uint8_t *__restrict__ slots, uint64_t stride,
+						     const uint32_t *__restrict__ len, uint32_t n,
+						     uint8_t *__restrict__ packed, const uint64_t *__restrict__ off)
+{
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+	for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+		const uint8_t *src = slots + (uint64_t)i * stride;
+		uint8_t *dst = packed + off[i];
+		const uint32_t m = len[i];
+		uint32_t head = (uint32_t)((4u - (reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u);
+		if (head > m)
+			head = m;
+		if (lane < head)
+			dst[lane] = src[lane];
+		const uint32_t words = (m - head) >> 2;
+		const uint8_t *s = src + head;
+		const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(s) & 3u);
+		const uint32_t *sw = reinterpret_cast<const uint32_t *>(s - sh);
+		uint32_t *dw = reinterpret_cast<uint32_t *>(dst + head);
+		if (sh == 0) {
+			for (uint32_t w = lane; w < words; w += 32)
+				dw[w] = sw[w];
+		} else {
+			// reads sw[w+1] only when it still overlaps [src, src+m): true because sh != 0
+			for (uint32_t w = lane; w < words; w += 32)
+				dw[w] = __funnelshift_r(sw[w], sw[w + 1], sh * 8);
+		}
+		const uint32_t tail = head + (words << 2);
+		if (tail + lane < m)
+			dst[tail + lane] = src[tail + lane];
+	}
+}
+
+}  // namespace csb
+
+using namespace csb;
+
+extern "C" uint64_t csb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+extern "C" int csb_launch_pack(const uint8_t *slots, uint64_t slot_stride, const uint32_t *len, uint32_t n_blocks,
+			       uint8_t *packed, uint64_t *off, csb_stream_t s)
+{
+	DeviceInfo di;
+	int e = device_info(&di);
+	if (e)
+		return e;
+	scan_kernel<<<1, kScanThreads, 0, s>>>(len, n_blocks, off);
+	count_launch();
+	if ((e = (int)cudaGetLastError()))
+		return e;
+	if (packed && n_blocks) {
+		long ctas = ((long)n_blocks + 7) / 8;
+		if (ctas > (long)di.sm_count * 8)
+			ctas = (long)di.sm_count * 8;
+		gather_kernel<<<(int)ctas, 256, 0, s>>>(slots, slot_stride, len, n_blocks, packed, off);
+		count_launch();
+		e = (int)cudaGetLastError();
+	}
+	return e;
+}

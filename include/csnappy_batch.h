@@ -1,0 +1,118 @@
+/*
+ * csnappy_batch.h -- batched entry points of the B200-native Snappy codec.
+ *
+ * These are the additions BASELINE.json's north_star asks for next to the
+ * csnappy.h drop-in: many independent blocks (zram 4 KiB pages,
+ * kernel_3_2_10.patch:1348-1372; block_compressor pages, block_compressor.c:
+ * 113-134, 307-335, 365-387; the 32 KiB fragments of csnappy_compress,
+ * csnappy_compress.c:636-654) handed to the GPU in ONE call.  Per block the
+ * semantics are exactly those of csnappy_compress_fragment /
+ * csnappy_decompress_noheader / csnappy_decompress.
+ *
+ * Pointers named d_* are DEVICE pointers on the current CUDA device, pointers
+ * named h_* are HOST pointers.  `stream` is a cudaStream_t passed as void*
+ * (NULL = the legacy default stream).  Device-pointer calls are asynchronous
+ * with respect to the host: they enqueue work on `stream` and return.
+ *
+ * Block i of a batch lives at
+ *     base + (off ? off[i] : i * stride)
+ * Strided outputs need  out_stride >= csnappy_max_compressed_length(len)  for
+ * compression (the compressor never bounds-checks its output, exactly like the
+ * reference, cl_tester.c:120-165) and >= capacity for decompression.
+ * Fast paths engage when base, stride and offsets are multiples of 16.
+ *
+ * Every function returns 0, CSNAPPY_E_DEVICE or CSNAPPY_E_BAD_ARG; per-block
+ * decoder results go to d_status[] / h_status[].
+ */
+#ifndef CSNAPPY_B200_CSNAPPY_BATCH_H_
+#define CSNAPPY_B200_CSNAPPY_BATCH_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "csnappy.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* flags */
+#define CSNAPPY_BATCH_SHRINK_TABLE 0x1u /* compress: per block, apply csnappy_compress()'s
+					   short-chunk table rule (csnappy_compress.c:638-646) */
+#define CSNAPPY_BATCH_WITH_HEADER 0x2u  /* decompress: blocks start with a varint32 length;
+					   csnappy_decompress() semantics incl. -1 / -2
+					   (csnappy_decompress.c:394-411) */
+
+/*
+ * Batched csnappy_compress_fragment (csnappy_compress.c:469-606).
+ *   d_in_len == NULL  => every block is uniform_in_len bytes.
+ *   d_out_len[i]      <- compressed size of block i.
+ * Block lengths must be <= 32768; 9 <= wm <= 16.
+ */
+int csnappy_batch_compress_fragments(const void *d_in, const uint64_t *d_in_off,
+				     uint64_t in_stride, const uint32_t *d_in_len,
+				     uint32_t uniform_in_len, uint32_t n_blocks,
+				     void *d_out, uint64_t out_stride,
+				     uint32_t *d_out_len,
+				     int workmem_bytes_power_of_two, uint32_t flags,
+				     void *stream);
+
+/*
+ * Batched csnappy_decompress_noheader (csnappy_decompress.c:319-387), or
+ * csnappy_decompress with CSNAPPY_BATCH_WITH_HEADER.
+ *   d_out_cap == NULL => every block has capacity uniform_out_cap.
+ *   d_status[i]       <- 0 / -1 / -2 / -3 / -5
+ *   d_out_len[i]      <- bytes produced when d_status[i] == 0, else 0.
+ */
+int csnappy_batch_decompress(const void *d_in, const uint64_t *d_in_off,
+			     uint64_t in_stride, const uint32_t *d_in_len,
+			     uint32_t n_blocks, void *d_out, uint64_t out_stride,
+			     const uint32_t *d_out_cap, uint32_t uniform_out_cap,
+			     uint32_t *d_out_len, int32_t *d_status, uint32_t flags,
+			     void *stream);
+
+/*
+ * Exclusive scan of d_len[0..n) into d_off[0..n] (d_off[n] = total) and
+ * gather of the strided slots into one contiguous payload:
+ *     d_packed[d_off[i] .. d_off[i]+d_len[i]) = d_slots[i*slot_stride ..)
+ * This is the size-gather + prefix-sum index of block_compressor.c:298-335 and
+ * the fragment concatenation of csnappy_compress.c:647-653, done on the device.
+ * d_packed may be NULL to compute offsets only.
+ */
+int csnappy_batch_pack(const void *d_slots, uint64_t slot_stride,
+		       const uint32_t *d_len, uint32_t n_blocks, void *d_packed,
+		       uint64_t *d_off, void *stream);
+
+/*
+ * Host-buffer variants: same semantics, HOST pointers, synchronous.  Pages are
+ * streamed through the device in chunks on several CUDA streams so that H2D,
+ * kernels and D2H overlap.  These are what a zram / block_compressor style
+ * caller with host memory uses, and what bench.py times as "e2e".
+ */
+int csnappy_batch_compress_fragments_host(const void *h_in, uint64_t in_stride,
+					  uint32_t uniform_in_len, uint32_t n_blocks,
+					  void *h_out, uint64_t out_stride,
+					  uint32_t *h_out_len,
+					  int workmem_bytes_power_of_two);
+
+int csnappy_batch_decompress_host(const void *h_in, uint64_t in_stride,
+				  const uint32_t *h_in_len, uint32_t n_blocks,
+				  void *h_out, uint64_t out_stride,
+				  uint32_t uniform_out_cap, uint32_t *h_out_len,
+				  int32_t *h_status, uint32_t flags);
+
+/*
+ * Library / device introspection and kernel tuning knobs (used by bench.py and
+ * the tests; not needed by drop-in callers).
+ */
+int csnappy_b200_device_ok(void);	   /* 1 if a CUDA device is usable */
+const char *csnappy_b200_last_error(void); /* text of the last device error (thread local) */
+uint64_t csnappy_b200_kernel_launches(void); /* kernels launched by this library so far */
+/* key: "compress_lanes" | "decompress_lanes" (lanes cooperating on one block: 8/16/32),
+ *      "ctas_per_sm" ; value 0 restores the default.  Returns 0 or CSNAPPY_E_BAD_ARG. */
+int csnappy_b200_set_tuning(const char *key, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSNAPPY_B200_CSNAPPY_BATCH_H_ */

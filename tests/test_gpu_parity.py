@@ -1,0 +1,314 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI (ctypes), against the oracle.
+
+Bit-exact bar: compressed bytes, produced bytes, lengths and return codes must be
+identical to the oracle's (the unmodified reference when oracle/_ref was built, else
+our pinned restatement) and to the committed golden vectors.  Mirrors the reference's
+own checks: `make cl_test` (Makefile:21-29), cl_tester -S d (cl_tester.c:167-238),
+baddata3 (Makefile:33), check_unaligned_uint64 (Makefile:37-55).
+"""
+import hashlib
+import struct
+
+import numpy as np
+import pytest
+
+import oracle
+from cases import fuzz_pages, synth_cases
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def sha(b):
+    return hashlib.sha256(b).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def cs():
+    import csnappy_b200 as c
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    assert c.device_ok(), c.api.last_error()
+    return c
+
+
+@pytest.fixture(scope="module")
+def chk():
+    return oracle.best()
+
+
+# --------------------------------------------------------------------------- drop-in API (host pointers)
+def test_dropin_compress_urls_wm15_equals_fixture(cs, urls, urls_snappy):
+    assert cs.csnappy_compress(urls, 15) == urls_snappy
+
+
+@pytest.mark.parametrize("wm", range(9, 17))
+def test_dropin_compress_urls_all_wm(cs, golden, urls, wm):
+    c = cs.csnappy_compress(urls, wm)
+    g = golden["compress_urls"][str(wm)]
+    assert (len(c), sha(c)) == (g["len"], g["sha256"])
+
+
+def test_dropin_roundtrip_urls(cs, urls, urls_snappy):
+    rc, out = cs.csnappy_decompress(urls_snappy, len(urls))
+    assert rc == 0 and out == urls
+    c16 = cs.csnappy_compress(urls, 16)
+    rc, out = cs.csnappy_decompress(c16, len(urls))
+    assert rc == 0 and out == urls
+
+
+def test_dropin_selftest_decompression(cs, chk):
+    """cl_tester.c:167-238: -2 on small dst, -3 from noheader with small capacity, cut literal != OK."""
+    rng = np.random.default_rng(1)
+    data = rng.integers(0, 256, 4096 + 100, dtype=np.uint8).tobytes()
+    comp = cs.csnappy_compress(data, 16)
+    assert comp == chk.compress(data, 16)
+    assert cs.csnappy_decompress(comp, 4096)[0] == cs.CSNAPPY_E_OUTPUT_INSUF
+    hlen, n = cs.csnappy_get_uncompressed_length(comp)
+    assert hlen > 0 and n == len(data)
+    assert cs.csnappy_decompress_noheader(comp[hlen:], 4096)[0] == cs.CSNAPPY_E_OUTPUT_OVERRUN
+    fake = bytes.fromhex("32c4666f6f6f6f6f6f")
+    assert cs.csnappy_decompress(fake, 50)[0] == cs.CSNAPPY_E_DATA_MALFORMED
+    assert cs.csnappy_decompress_noheader(fake[1:], 50)[0] == cs.CSNAPPY_E_DATA_MALFORMED
+
+
+def test_dropin_baddata3(cs, golden, baddata3):
+    rc, _ = cs.csnappy_decompress(baddata3, golden["baddata3"]["header_len"])
+    assert rc == golden["baddata3"]["rc"] == -5
+
+
+def test_dropin_unaligned_uint64(cs, unaligned_pair):
+    comp, expect = unaligned_pair
+    rc, out = cs.csnappy_decompress(comp, len(expect))
+    assert rc == 0 and out == expect
+
+
+def test_dropin_decode_matrix(cs, golden):
+    for e in golden["decode_noheader"]:
+        rc, out = cs.csnappy_decompress_noheader(bytes.fromhex(e["hex"]), e["cap"])
+        assert rc == e["rc"], e
+        if rc == 0:
+            assert out.hex() == e["out_hex"], e
+    for e in golden["decode_header"]:
+        assert cs.csnappy_decompress(bytes.fromhex(e["hex"]), e["dst_len"])[0] == e["rc"], e
+    for hx in ("0861626301", "0861626302", "086162630203", "086162630f0300", "f0", "f4ff"):
+        assert cs.csnappy_decompress_noheader(bytes.fromhex(hx), 100)[0] == -5, hx
+
+
+def test_dropin_tiny_and_synth(cs, golden):
+    for label, g in golden["tiny"].items():
+        assert cs.csnappy_compress(bytes.fromhex(g["input_hex"]), 16).hex() == g["wm16_hex"], label
+    for name, data in synth_cases().items():
+        g = golden["synth"][name]
+        for wm in (9, 13, 15, 16):
+            c = cs.csnappy_compress_fragment(data, wm)
+            assert (len(c), sha(c)) == (g[f"frag_wm{wm}"]["len"], g[f"frag_wm{wm}"]["sha256"]), (name, wm)
+            assert cs.csnappy_decompress_noheader(c, len(data)) == (0, data), (name, wm)
+
+
+def test_dropin_multichunk_sizes(cs, chk):
+    rng = np.random.default_rng(3)
+    text = bytes(rng.integers(97, 101, 200000, dtype=np.uint8))
+    for n in (0, 1, 14, 15, 32767, 32768, 32769, 65536, 70001, 150000):
+        for wm in (9, 13, 16):
+            c = cs.csnappy_compress(text[:n], wm)
+            assert c == chk.compress(text[:n], wm), (n, wm)
+            assert cs.csnappy_decompress(c, n) == (0, text[:n])
+
+
+# --------------------------------------------------------------------------- device batches
+def _to_dev(pages, stride):
+    B = len(pages)
+    host = np.zeros((B, stride), dtype=np.uint8)
+    lens = np.zeros(B, dtype=np.int32)
+    for i, p in enumerate(pages):
+        host[i, : len(p)] = np.frombuffer(p, dtype=np.uint8)
+        lens[i] = len(p)
+    return torch.from_numpy(host).cuda(), torch.from_numpy(lens).cuda(), host, lens
+
+
+def _gpu_compress(cs, pages, block, wm, lanes=0, var_len=False):
+    cs.set_tuning("compress_lanes", lanes)
+    try:
+        d_in, d_len, _, _ = _to_dev(pages, block)
+        out, out_len = cs.batch_compress_fragments(d_in, block, len(pages), wm, in_len=d_len if var_len else None)
+        torch.cuda.synchronize()
+    finally:
+        cs.set_tuning("compress_lanes", 0)
+    ostride = cs.api.out_stride_for(block)
+    o = out.cpu().numpy().reshape(-1)[: len(pages) * ostride].reshape(len(pages), ostride)
+    ln = out_len.cpu().numpy().astype(np.uint32)
+    return [o[i, : ln[i]].tobytes() for i in range(len(pages))], out, out_len
+
+
+@pytest.mark.parametrize("lanes", [32, 16, 8])
+@pytest.mark.parametrize("key", ["4096/13", "32768/15", "32768/16", "4096/9", "4096/16"])
+def test_batch_compress_urls_fragments(cs, golden, urls, key, lanes):
+    block, wm = map(int, key.split("/"))
+    pages = [urls[o:o + block] for o in range(0, len(urls), block)]
+    comp, _, _ = _gpu_compress(cs, pages, block, wm, lanes, var_len=True)
+    stream = b"".join(struct.pack("<I", len(c)) + c for c in comp)
+    g = golden["fragments_urls"][key]
+    assert (len(comp), sum(map(len, comp)), sha(stream)) == (g["blocks"], g["total"], g["sha256"])
+
+
+@pytest.mark.parametrize("lanes", [32, 16, 8])
+@pytest.mark.parametrize("size,wm", [(4096, 13), (4096, 9), (32768, 15), (32768, 16), (1000, 12), (20000, 14), (64, 10)])
+def test_batch_compress_fuzz_vs_oracle(cs, chk, size, wm, lanes):
+    pages = fuzz_pages(4321 + size + wm, 70, size)
+    comp, _, _ = _gpu_compress(cs, pages, size, wm, lanes)
+    for i, (p, c) in enumerate(zip(pages, comp)):
+        assert c == chk.compress_fragment(p, wm), (i, size, wm, lanes)
+
+
+def test_batch_compress_edge_sizes(cs, chk):
+    rng = np.random.default_rng(7)
+    text = bytes(rng.integers(97, 101, 40000, dtype=np.uint8))
+    sizes = list(range(0, 40)) + [59, 60, 61, 62, 255, 256, 257, 258] + list(range(4081, 4112)) + list(range(32753, 32769))
+    pages = [text[:n] for n in sizes]
+    for wm in (9, 13, 16):
+        comp, _, _ = _gpu_compress(cs, pages, 32768, wm, var_len=True)
+        for n, c in zip(sizes, comp):
+            assert c == chk.compress_fragment(text[:n], wm), (n, wm)
+
+
+def test_batch_compress_shrink_table_flag(cs, chk):
+    rng = np.random.default_rng(8)
+    text = bytes(rng.integers(97, 103, 32768, dtype=np.uint8))
+    sizes = [100, 255, 256, 257, 4096, 4097, 13959, 32767, 32768]
+    d_in, d_len, _, _ = _to_dev([text[:n] for n in sizes], 32768)
+    out, out_len = cs.batch_compress_fragments(d_in, 32768, len(sizes), 16, in_len=d_len, flags=cs.api.BATCH_SHRINK_TABLE)
+    torch.cuda.synchronize()
+    ostride = cs.api.out_stride_for(32768)
+    o = out.cpu().numpy()
+    for i, n in enumerate(sizes):
+        got = o[i * ostride: i * ostride + int(out_len[i])].tobytes()
+        assert got == chk.compress_fragment(text[:n], oracle.port().chunk_wm(n, 16)), n
+
+
+@pytest.mark.parametrize("lanes", [32, 16, 8])
+def test_batch_decompress_roundtrip_and_errors(cs, chk, lanes):
+    pages = fuzz_pages(99, 140, 4096)
+    comp = [chk.compress_fragment(p, 13) for p in pages]
+    rng = np.random.default_rng(5)
+    streams, caps = [], []
+    for i, c in enumerate(comp):
+        d = bytearray(c)
+        k = i % 5
+        if k == 1 and len(d) > 8:
+            d[int(rng.integers(0, len(d)))] ^= int(rng.integers(1, 256))
+        elif k == 2 and len(d) > 8:
+            d = d[: int(rng.integers(1, len(d)))]
+        streams.append(bytes(d))
+        caps.append(4096 if k != 3 else 2000)
+    stride = cs.csnappy_max_compressed_length(4096) + 6
+    stride = (stride + 15) // 16 * 16
+    d_in, d_len, _, _ = _to_dev(streams, stride)
+    d_caps = torch.tensor(caps, dtype=torch.int32).cuda()
+    cs.set_tuning("decompress_lanes", lanes)
+    try:
+        out, out_len, status = cs.batch_decompress(d_in, d_len, len(streams), 4096, in_stride=stride, out_caps=d_caps,
+                                                   out_stride=4096)
+        torch.cuda.synchronize()
+    finally:
+        cs.set_tuning("decompress_lanes", 0)
+    o, ol, st = out.cpu().numpy(), out_len.cpu().numpy(), status.cpu().numpy()
+    n_err = 0
+    for i, s in enumerate(streams):
+        rc, exp = oracle.port().decompress_noheader(s, caps[i])  # the port defines the truncated-tag case as -5
+        assert st[i] == rc, (i, s.hex()[:80])
+        if rc == 0:
+            assert ol[i] == len(exp) and o[i * 4096: i * 4096 + ol[i]].tobytes() == exp, i
+        else:
+            n_err += 1
+            assert ol[i] == 0
+    assert n_err > 20
+
+
+def test_batch_decompress_with_header_and_streaming_path(cs, chk, urls, urls_snappy, baddata3, unaligned_pair):
+    """Whole multi-chunk streams in one batch: exercises the global-memory path and -1/-2."""
+    uu_s, uu_b = unaligned_pair
+    streams = [urls_snappy, baddata3, uu_s, b"", bytes.fromhex("80"), chk.compress(urls[:5000], 16), urls_snappy]
+    caps = [len(urls), 130378, len(uu_b), 10, 10, 5000, 4096]
+    expect_rc = [0, -5, 0, -1, -1, 0, -2]
+    off = np.zeros(len(streams), dtype=np.int64)
+    pos = 0
+    for i, s in enumerate(streams):
+        off[i] = pos
+        pos += (len(s) + 15) // 16 * 16 + 16
+    host = np.zeros(pos, dtype=np.uint8)
+    for i, s in enumerate(streams):
+        host[off[i]: off[i] + len(s)] = np.frombuffer(s, dtype=np.uint8)
+    d_in = torch.from_numpy(host).cuda()
+    d_off = torch.from_numpy(off).cuda()
+    d_len = torch.tensor([len(s) for s in streams], dtype=torch.int32).cuda()
+    d_caps = torch.tensor(caps, dtype=torch.int32).cuda()
+    ostride = (max(caps) + 15) // 16 * 16
+    out, out_len, status = cs.batch_decompress(d_in, d_len, len(streams), 0, in_off=d_off, out_caps=d_caps,
+                                               out_stride=ostride, flags=cs.api.BATCH_WITH_HEADER)
+    torch.cuda.synchronize()
+    st, ol, o = status.cpu().numpy(), out_len.cpu().numpy(), out.cpu().numpy()
+    assert list(st) == expect_rc
+    assert o[: ol[0]].tobytes() == urls
+    assert o[2 * ostride: 2 * ostride + ol[2]].tobytes() == uu_b
+    assert o[5 * ostride: 5 * ostride + ol[5]].tobytes() == urls[:5000]
+
+
+def test_batch_pack(cs):
+    rng = np.random.default_rng(11)
+    n, stride = 1000, 4816
+    lens = rng.integers(0, 4811, n).astype(np.int32)
+    lens[:5] = [0, 1, 3, 4810, 17]
+    slots = rng.integers(0, 256, (n, stride), dtype=np.uint8)
+    d_slots = torch.from_numpy(slots).cuda()
+    d_len = torch.from_numpy(lens).cuda()
+    packed, off = cs.batch_pack(d_slots, stride, d_len, n)
+    torch.cuda.synchronize()
+    off = off.cpu().numpy()
+    assert (off[:-1] == np.concatenate([[0], np.cumsum(lens.astype(np.int64))[:-1]])).all() and off[-1] == lens.sum()
+    p = packed.cpu().numpy()
+    for i in range(n):
+        assert (p[off[i]: off[i] + lens[i]] == slots[i, : lens[i]]).all(), i
+
+
+# --------------------------------------------------------------------------- host batches + scale properties
+def test_host_batch_roundtrip(cs, chk):
+    pages = fuzz_pages(2024, 3000, 4096)
+    B = len(pages)
+    h_in = np.frombuffer(b"".join(pages), dtype=np.uint8).reshape(B, 4096)
+    ostride = cs.api.out_stride_for(4096)
+    h_out = np.zeros((B, ostride), dtype=np.uint8)
+    h_len = np.zeros(B, dtype=np.uint32)
+    cs.batch_compress_fragments_host(h_in, 4096, B, 13, h_out, h_len)
+    for i in range(0, B, 37):
+        assert h_out[i, : h_len[i]].tobytes() == chk.compress_fragment(pages[i], 13), i
+    back = np.zeros((B, 4096), dtype=np.uint8)
+    blen = np.zeros(B, dtype=np.uint32)
+    st = np.ones(B, dtype=np.int32)
+    cs.batch_decompress_host(h_out, ostride, h_len, B, back, 4096, 4096, blen, st)
+    assert (st == 0).all() and (blen == 4096).all() and (back == h_in).all()
+
+
+def test_scale_mixed_pages_roundtrip_and_oracle_sample(cs, chk):
+    """256 Ki mixed 4 KiB pages (1 GiB): round trip on the device, oracle check of a sample,
+    and the checksum-of-lengths property against the CPU harness on a 16 Ki page prefix."""
+    from csnappy_b200 import synth
+
+    B = 1 << 18
+    d_pages = synth.mixed_pages(B, 4096, seed=0x5EED0001, device="cuda")
+    out, out_len = cs.batch_compress_fragments(d_pages, 4096, B, 13)
+    ostride = cs.api.out_stride_for(4096)
+    back, back_len, status = cs.batch_decompress(out, out_len, B, 4096, in_stride=ostride)
+    torch.cuda.synchronize()
+    assert int((status != 0).sum()) == 0
+    assert int((back_len != 4096).sum()) == 0
+    assert torch.equal(back.view(B, 4096), d_pages.view(B, 4096))
+    S = 1 << 14
+    host = d_pages.view(B, 4096)[:S].cpu().numpy()
+    ref_out, ref_len, _ = oracle.batch_compress(host, 13, chk.kind, threads=4)
+    got_len = out_len[:S].cpu().numpy().astype(np.uint32)
+    assert (got_len == ref_len).all()
+    got = out.view(B, ostride)[:S].cpu().numpy()
+    mask = np.arange(ostride)[None, :] < ref_len[:, None]
+    assert (got[mask] == ref_out[:, :ostride][mask]).all()
