@@ -175,6 +175,8 @@ def main():
     ap.add_argument("--lanes-c", type=int, default=0)
     ap.add_argument("--lanes-d", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--only", default="", choices=["", "text", "zero", "random"],
+                    help="diagnostic: make every page of one class (not the BASELINE workload)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -208,7 +210,7 @@ def main():
 
     B = args.pages
     first, _ = shard.block_range(B * world, rank, world)  # weak scaling: rank r owns pages [r*B, (r+1)*B)
-    pages = synth.mixed_pages(B, PAGE, seed=SEED, device=dev, first_page=first)
+    pages = synth.mixed_pages(B, PAGE, seed=SEED, device=dev, first_page=first, only=args.only)
     ostride = cs.api.out_stride_for(PAGE)
     comp = torch.empty(B * ostride, dtype=torch.uint8, device=dev)
     comp_len = torch.empty(B, dtype=torch.int32, device=dev)

@@ -2,337 +2,383 @@
 //
 // Produces, for every block, exactly the bytes csnappy_compress_fragment produces
 // (/root/reference/csnappy_compress.c:469-606) for the same input and table size.
+//
 // The reference's greedy parse is a serial dependency chain (every probe reads and
-// overwrites a hash slot), so parallelism comes from three places only:
-//   * blocks are independent: one GROUP of G lanes per block, ~18 blocks resident per SM
-//     (bounded by shared memory: u16 hash table of 1<<wm bytes + the staged input);
-//   * inside a scan, the next G probe positions are data independent (they depend only on
-//     the skip counter, csnappy_compress.c:535-542), so G lanes probe them speculatively,
-//     resolve same-hash collisions with match.any, find the first hit with ballot/ffs and
-//     commit only the table writes the serial code would have made;
-//   * match extension compares 4*G bytes per step, copy tags of long matches and literal
-//     payloads are emitted by all lanes.
-// Output is staged in a small shared-memory ring and flushed to HBM in 16-byte units.
+// overwrites a hash slot), so the kernel is bound by instruction issue and shared-memory
+// latency, not by HBM (profiles/).  The design therefore minimises warp instructions per
+// block and keeps every resident block busy:
+//
+//   * one GROUP of G lanes (8, 16 or 32: a slice of one warp) per block; a persistent CTA per
+//     SM holds as many groups as shared memory allows (u16 hash table of 1<<wm bytes + the
+//     staged input: 18 x 4 KiB pages per SM at wm 13); groups claim blocks from a global counter;
+//   * the block is staged with ONE bulk async copy (cp.async.bulk -> UBLKCP, completion on an
+//     mbarrier) issued by one lane while the group clears its hash table;
+//   * the whole parse is ONE uniform loop of "probe steps".  A probe step evaluates G
+//     consecutive probe positions of the reference's scan at once -- they depend only on the
+//     skip counter (csnappy_compress.c:535-542) -- resolves equal-hash lanes with match.any,
+//     finds the first hit with ballot/ffs and commits exactly the table writes the serial code
+//     would have made.  The post-copy bookkeeping of the reference (insert ip-1, re-probe ip,
+//     csnappy_compress.c:587-593) is folded into the same step: lane 0 inserts ip-1, lane 1
+//     probes ip, lanes 2.. already run the next scan from ip+1, because that is exactly the
+//     order in which the serial code touches the table;
+//   * match extension compares 4*G bytes per step and reduces with redux.min; literals and
+//     copy tags are written straight to the block's HBM slot with lane-parallel byte stores
+//     (L2 merges them; the kernel is nowhere near the HBM roofline);
+//   * the per-group control flow is a flat state machine (claim / wait for the bulk copy /
+//     step), so the groups sharing a warp never wait for each other at block boundaries.
 #include "device_common.cuh"
 #include "kernels.h"
 
 namespace csb {
 
-constexpr uint32_t kRing = 512;	     // output staging ring per group (bytes, power of two)
-constexpr uint32_t kAppendMax = 256; // largest single append into the ring
 constexpr uint32_t kInPad = 32;	     // slack after the staged input for 4-byte over-reads
 constexpr uint32_t kTailMargin = 15; // kInputMarginBytes, csnappy_compress.c:468
+constexpr int kMaxThreads = 640;
 
 struct CompressParams {
 	csb_compress_args a;
-	uint32_t *counter;     // dynamic block claim; NULL => static striding
+	uint32_t *counter;     // dynamic block claim
 	uint32_t table_bytes;  // 1 << wm
-	uint32_t in_area;      // bytes reserved for the staged input (multiple of 16)
-	uint32_t group_smem;   // table_bytes + in_area + kRing
+	uint32_t in_area;      // bytes reserved for the staged input incl. pad (multiple of 16)
+	uint32_t group_smem;   // table_bytes + in_area + 16 (mbarrier)
 	uint32_t groups;       // groups per CTA that own shared memory
 };
 
+// ---- output: lane-parallel byte stores into the block's HBM slot ----------------------------
+
+// literal tag + payload, csnappy_compress.c:332-371.  Returns bytes written.
 template <int G>
-struct Emitter {
-	const Group<G> &g;
-	uint8_t *ring;
-	uint8_t *dst;	   // block's output slot in HBM
-	uint32_t op;	   // bytes emitted so far
-	uint32_t flushed;  // bytes already written to HBM (multiple of 16 while vec is true)
-	bool vec;	   // dst is 16-byte aligned
-
-	__device__ __forceinline__ Emitter(const Group<G> &g_, uint8_t *ring_, uint8_t *dst_)
-		: g(g_), ring(ring_), dst(dst_), op(0), flushed(0)
-	{
-		vec = (reinterpret_cast<uintptr_t>(dst_) & 15u) == 0;
+__device__ __forceinline__ uint32_t emit_literal(const Group<G> &g, uint8_t *dst, const uint8_t *sin, uint32_t src,
+						 uint32_t len)
+{
+	const uint32_t v = len - 1;
+	uint32_t hb, hdr;
+	if (v < 60) {
+		hb = 1;
+		hdr = v << 2;
+	} else if (v < 256) {
+		hb = 2;
+		hdr = (60u << 2) | (v << 8);
+	} else {
+		hb = 3;
+		hdr = (61u << 2) | (v << 8);
 	}
-
-	// write out every complete 16-byte unit (vec) or every pending byte (!vec)
-	__device__ __forceinline__ void flush()
-	{
-		g.sync();
-		if (vec) {
-			const uint32_t units = (op - flushed) >> 4;
-			for (uint32_t u = g.lane; u < units; u += G) {
-				const uint32_t at = flushed + (u << 4);
-				stg_stream(reinterpret_cast<uint4 *>(dst + at),
-					   *reinterpret_cast<const uint4 *>(ring + (at & (kRing - 1))));
-			}
-			flushed += units << 4;
-		} else {
-			for (uint32_t at = flushed + g.lane; at < op; at += G)
-				dst[at] = ring[at & (kRing - 1)];
-			flushed = op;
-		}
-		g.sync();
+	const uint32_t total = hb + len;
+	if (total <= (uint32_t)G) {
+		// common case: header and payload in one store
+		if (g.lane < total)
+			dst[g.lane] = g.lane < hb ? (uint8_t)(hdr >> (8 * g.lane)) : sin[src + g.lane - hb];
+		return total;
 	}
-
-	__device__ __forceinline__ void reserve(uint32_t k)
-	{
-		if (op - flushed + k > kRing)
-			flush();
+	if (g.lane < hb)
+		dst[g.lane] = (uint8_t)(hdr >> (8 * g.lane));
+	dst += hb;
+	if (len <= 4u * G) {
+		for (uint32_t i = g.lane; i < len; i += G)
+			dst[i] = sin[src + i];
+	} else {
+		// word stores: head bytes up to a 4-byte aligned destination, realigned source words, tail
+		const uint32_t head = (uint32_t)(-(intptr_t)dst) & 3u;
+		if (g.lane < head)
+			dst[g.lane] = sin[src + g.lane];
+		const uint32_t words = (len - head) >> 2;
+		uint32_t *dw = reinterpret_cast<uint32_t *>(dst + head);
+		for (uint32_t w = g.lane; w < words; w += G)
+			dw[w] = lds32u(sin, src + head + 4 * w);
+		const uint32_t tail = head + (words << 2);
+		if (tail + g.lane < len)
+			dst[tail + g.lane] = sin[src + tail + g.lane];
 	}
+	return total;
+}
 
-	__device__ __forceinline__ void finish()
-	{
-		flush();
-		for (uint32_t at = flushed + g.lane; at < op; at += G)
-			dst[at] = ring[at & (kRing - 1)];
+// one copy element as a little-endian word + its size (2 or 3), csnappy_compress.c:373-393
+__device__ __forceinline__ uint32_t copy_piece(uint32_t offset, uint32_t len, uint32_t *nb)
+{
+	if (len < 12 && offset < 2048) {
+		*nb = 2;
+		return 1u | ((len - 4) << 2) | ((offset >> 8) << 5) | ((offset & 0xff) << 8);
 	}
+	*nb = 3;
+	return 2u | ((len - 1) << 2) | (offset << 8);
+}
 
-	__device__ __forceinline__ void put(uint32_t at, uint32_t byte) { ring[at & (kRing - 1)] = (uint8_t)byte; }
-
-	// literal tag + payload, csnappy_compress.c:332-371
-	__device__ __forceinline__ void literal(const uint8_t *sin, uint32_t src, uint32_t len)
-	{
-		const uint32_t v = len - 1;
-		uint32_t first = len < kAppendMax - 3 ? len : kAppendMax - 3;
-		reserve(3 + first);
-		uint32_t hb;
-		if (v < 60) {
-			hb = 1;
-			if (g.lane == 0)
-				put(op, v << 2);
-		} else if (v < 256) {
-			hb = 2;
-			if (g.lane == 0) {
-				put(op, 60u << 2);
-				put(op + 1, v);
-			}
-		} else {
-			hb = 3;
-			if (g.lane == 0) {
-				put(op, 61u << 2);
-				put(op + 1, v & 0xff);
-				put(op + 2, v >> 8);
-			}
-		}
-		op += hb;
-		for (;;) {
-			for (uint32_t i = g.lane; i < first; i += G)
-				put(op + i, sin[src + i]);
-			op += first;
-			src += first;
-			len -= first;
-			if (len == 0)
-				break;
-			first = len < kAppendMax ? len : kAppendMax;
-			reserve(first);
-		}
-	}
-
-	// one copy element at ring position `at`; returns its size (2 or 3), csnappy_compress.c:373-393
-	__device__ __forceinline__ uint32_t copy_piece(uint32_t at, uint32_t offset, uint32_t len, bool write)
-	{
-		if (len < 12 && offset < 2048) {
-			if (write) {
-				put(at, 1u | ((len - 4) << 2) | ((offset >> 8) << 5));
-				put(at + 1, offset & 0xff);
-			}
-			return 2;
-		}
-		if (write) {
-			put(at, 2u | ((len - 1) << 2));
-			put(at + 1, offset & 0xff);
-			put(at + 2, offset >> 8);
-		}
-		return 3;
-	}
-
-	// split rule of csnappy_compress.c:395-415: 64s while len >= 68, one 60 if len > 64, the rest
-	__device__ __forceinline__ void copy(uint32_t offset, uint32_t len)
-	{
-		if (len <= 64) {
-			reserve(3);
-			op += copy_piece(op, offset, len, g.lane == 0);
-			return;
-		}
+// split rule of csnappy_compress.c:395-415: 64s while len >= 68, one 60 if len > 64, the rest
+template <int G>
+__device__ __forceinline__ uint32_t emit_copy(const Group<G> &g, uint8_t *dst, uint32_t offset, uint32_t len)
+{
+	uint32_t done = 0;
+	if (len > 64) {
 		const uint32_t q = len >= 68 ? (len - 68) / 64 + 1 : 0;
 		uint32_t rem = len - 64 * q;  // 4..67
 		const uint32_t n60 = rem > 64 ? 1 : 0;
 		rem -= 60 * n60;
 		const uint32_t lead = q + n60;	// all 3-byte copy-2 elements
-		for (uint32_t t0 = 0; t0 < lead; t0 += G) {
-			reserve(3 * G);
-			const uint32_t t = t0 + g.lane;
-			if (t < lead)
-				copy_piece(op + 3 * g.lane, offset, t < q ? 64 : 60, true);
-			const uint32_t done = lead - t0 < (uint32_t)G ? lead - t0 : (uint32_t)G;
-			op += 3 * done;
+		for (uint32_t t = g.lane; t < lead; t += G) {
+			const uint32_t w = 2u | (((t < q ? 64u : 60u) - 1) << 2) | (offset << 8);
+			uint8_t *d = dst + 3 * t;
+			d[0] = (uint8_t)w;
+			d[1] = (uint8_t)(w >> 8);
+			d[2] = (uint8_t)(w >> 16);
 		}
-		reserve(3);
-		op += copy_piece(op, offset, rem, g.lane == 0);
+		done = 3 * lead;
+		len = rem;
 	}
-};
-
-template <int G>
-__device__ __forceinline__ void compress_block(const Group<G> &g, const CompressParams &p, uint32_t blk,
-					       uint16_t *tab, uint8_t *sin, uint8_t *ring)
-{
-	const csb_compress_args &a = p.a;
-	const uint64_t in_at = a.in_off ? a.in_off[blk] : (uint64_t)blk * a.in_stride;
-	uint32_t n = a.in_len ? a.in_len[blk] : a.uniform_len;
-	if (a.total_len) {
-		const uint64_t left = a.total_len > in_at ? a.total_len - in_at : 0;
-		if (left < n)
-			n = (uint32_t)left;
-	}
-	if (n > CSB_FRAGMENT_MAX)
-		n = CSB_FRAGMENT_MAX;  // REQUIRES of the reference (csnappy.h:38); launcher rejects uniform_len above it
-	const uint8_t *src = a.in + in_at;
-	Emitter<G> em(g, ring, a.out + (uint64_t)blk * a.out_stride);
-
-	// table size for this block (csnappy_compress.c:638-646 when SHRINK_TABLE is set)
-	int ws = a.wm;
-	if ((a.flags & 1u) && n < CSB_FRAGMENT_MAX) {
-		for (ws = 9; ws < a.wm; ++ws)
-			if ((1u << (ws - 1)) >= n)
-				break;
-	}
-	const int shift = 33 - ws;
-
-	g.sync();  // previous block's readers of sin/tab/ring are done
-	load_block_to_smem<G>(g, sin, src, n);
-	if (n >= kTailMargin) {	 // zero the table, csnappy_compress.c:501
-		uint4 *t4 = reinterpret_cast<uint4 *>(tab);
-		const uint32_t nv = (1u << ws) >> 4;
-		const uint4 z = make_uint4(0, 0, 0, 0);
-		for (uint32_t i = g.lane; i < nv; i += G)
-			t4[i] = z;
-	}
-	g.sync();
-
-	uint32_t next_emit = 0;
-	if (n >= kTailMargin) {
-
-		const uint32_t ip_limit = n - kTailMargin;
-		uint32_t ip = 1;
-		for (;;) {
-			// ---- scan: G speculative probes per step (csnappy_compress.c:535-552) ----
-			uint32_t base = ip, j = 0, cand = 0;
-			bool found = false;
-			for (;;) {
-				const uint32_t stride = (32u + j) >> 5;
-				const uint32_t pp = base + g.lane * stride;
-				const bool valid = pp + stride <= ip_limit;
-				uint32_t bytes = 0, h = 0x80000000u | g.lane, cb = 1;
-				if (valid) {
-					bytes = lds32u(sin, pp);
-					h = (bytes * kHashMul) >> shift;
-				}
-				const unsigned same = g.match(h);
-				const unsigned lower = same & ((1u << g.lane) - 1u);
-				if (valid) {
-					cand = lower ? base + (31 - __clz(lower)) * stride : tab[h];
-					cb = lds32u(sin, cand);
-				}
-				const unsigned hits = g.ballot(valid && cb == bytes);
-				const unsigned valids = g.ballot(valid);
-				const unsigned f = hits ? __ffs(hits) - 1 : (unsigned)G;
-				if (valid && g.lane <= f) {
-					// highest lane of an equal-hash run (up to the hit) owns the slot
-					const unsigned above = (same >> g.lane) >> 1;
-					const unsigned span = f - g.lane;
-					const unsigned rivals = span >= 32 ? above : (above & ((1u << span) - 1u));
-					if (!rivals)
-						tab[h] = (uint16_t)pp;
-				}
-				g.sync();
-				if (hits) {
-					ip = base + f * stride;
-					cand = g.bcast(cand, (int)f);
-					found = true;
-					break;
-				}
-				if (valids != ((G == 32) ? 0xffffffffu : ((1u << G) - 1u)))
-					break;	// ran into ip_limit without a hit
-				base += G * stride;
-				j += G;
-			}
-			if (!found)
-				break;
-
-			// ---- emit literal, then copies while the next position matches (:560-594) ----
-			em.literal(sin, next_emit, ip - next_emit);
-			bool again;
-			do {
-				// match extension: 4*G bytes per step, bounded by n (csnappy_compress.c:252-295)
-				uint32_t m = 4;
-				for (;;) {
-					const uint32_t at = ip + m + 4 * g.lane;
-					uint32_t mb = 0;
-					if (at < n) {
-						const uint32_t room = n - at;
-						const uint32_t x = lds32u(sin, cand + m + 4 * g.lane) ^ lds32u(sin, at);
-						mb = x ? (uint32_t)(__ffs(x) - 1) >> 3 : 4u;
-						if (mb > room)
-							mb = room;
-					}
-					const unsigned stop = g.ballot(mb < 4);
-					if (stop) {
-						const int fl = __ffs(stop) - 1;
-						m += 4 * fl + g.bcast(mb, fl);
-						break;
-					}
-					m += 4 * G;
-				}
-				em.copy(ip - cand, m);
-				ip += m;
-				next_emit = ip;
-				if (ip >= ip_limit)
-					goto remainder;
-				// insert ip-1, then probe ip (csnappy_compress.c:587-593); every lane does it
-				// redundantly: identical values to identical addresses
-				const uint32_t prev = lds32u(sin, ip - 1);
-				tab[(prev * kHashMul) >> shift] = (uint16_t)(ip - 1);
-				g.sync();
-				const uint32_t cur = lds32u(sin, ip);
-				const uint32_t hc = (cur * kHashMul) >> shift;
-				cand = tab[hc];
-				g.sync();
-				tab[hc] = (uint16_t)ip;
-				again = lds32u(sin, cand) == cur;
-				g.sync();
-			} while (again);
-			ip += 1;
-		}
-	}
-remainder:
-	if (next_emit < n)
-		em.literal(sin, next_emit, n - next_emit);
-	em.finish();
-	if (g.lane == 0)
-		a.out_len[blk] = em.op;
+	uint32_t nb;
+	const uint32_t w = copy_piece(offset, len, &nb);
+	if (g.lane < nb)
+		dst[done + g.lane] = (uint8_t)(w >> (8 * g.lane));
+	return done + nb;
 }
 
+// ---- the kernel ------------------------------------------------------------------------------
+
+enum : int { ST_NEED = 0, ST_LOADING = 1, ST_RUN = 2 };
+
 template <int G>
-__global__ void __launch_bounds__(1024) compress_kernel(const CompressParams p)
+__global__ void __launch_bounds__(kMaxThreads) compress_kernel(const CompressParams p)
 {
-	extern __shared__ __align__(16) uint8_t smem[];
+	extern __shared__ __align__(128) uint8_t smem[];
 	const Group<G> g;
-	const uint32_t groups_per_cta = p.groups;
 	const uint32_t gid = threadIdx.x / G;
 	if (gid >= p.groups)
 		return;	 // padding lanes of the last warp (no block-wide barriers in this kernel)
+	const csb_compress_args &a = p.a;
 	uint8_t *gs = smem + (size_t)gid * p.group_smem;
 	uint16_t *tab = reinterpret_cast<uint16_t *>(gs);
 	uint8_t *sin = gs + p.table_bytes;
-	uint8_t *ring = sin + p.in_area;
+	const uint32_t bar = smem_u32(sin + p.in_area);
+	const unsigned full = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
 
-	if (p.counter) {
-		for (;;) {
-			uint32_t blk = 0;
+	if (g.lane == 0) {
+		mbar_init(bar, 1);
+		fence_mbar_init();
+	}
+	g.sync();
+
+	int state = ST_NEED;
+	uint32_t parity = 0;
+	// per-block state
+	uint32_t blk = 0, n = 0, ip_limit = 0, op = 0, next_emit = 0, wbase = 1, t = 0;
+	int shift = 0, j0 = 0;
+	uint8_t *dst = nullptr;
+
+	for (;;) {
+		if (state == ST_NEED) {
 			if (g.lane == 0)
 				blk = atomicAdd(p.counter, 1u);
 			blk = g.bcast(blk, 0);
-			if (blk >= p.a.n_blocks)
+			if (blk >= a.n_blocks)
 				break;
-			compress_block<G>(g, p, blk, tab, sin, ring);
+			const uint64_t in_at = a.in_off ? a.in_off[blk] : (uint64_t)blk * a.in_stride;
+			n = a.in_len ? a.in_len[blk] : a.uniform_len;
+			if (a.total_len) {
+				const uint64_t left = a.total_len > in_at ? a.total_len - in_at : 0;
+				if (left < n)
+					n = (uint32_t)left;
+			}
+			if (n > CSB_FRAGMENT_MAX)
+				n = CSB_FRAGMENT_MAX;  // REQUIRES of the reference (csnappy.h:38)
+			const uint8_t *src = a.in + in_at;
+			dst = a.out + (uint64_t)blk * a.out_stride;
+			// table size for this block (csnappy_compress.c:638-646 when SHRINK_TABLE is set)
+			int ws = a.wm;
+			if ((a.flags & 1u) && n < CSB_FRAGMENT_MAX) {
+				for (ws = 9; ws < a.wm; ++ws)
+					if ((1u << (ws - 1)) >= n)
+						break;
+			}
+			shift = 33 - ws;
+			ip_limit = n >= kTailMargin ? n - kTailMargin : 0;
+			op = 0;
+			next_emit = 0;
+			wbase = 1;
+			j0 = 0;
+			t = 0;
+
+			g.sync();  // every lane is done with the previous block's input and table
+			const bool bulk = (reinterpret_cast<uintptr_t>(src) & 15u) == 0 && n >= 16;
+			const uint32_t n16 = bulk ? (n & ~15u) : 0;
+			if (bulk && g.lane == 0) {
+				fence_proxy_async();  // generic-proxy reads of sin precede the async-proxy write
+				mbar_expect_tx(bar, n16);
+				bulk_g2s(smem_u32(sin), src, n16, bar);
+			}
+			if (n >= kTailMargin) {	 // zero the table, csnappy_compress.c:501
+				uint4 *t4 = reinterpret_cast<uint4 *>(tab);
+				const uint32_t nv = (1u << ws) >> 4;
+				const uint4 z = make_uint4(0, 0, 0, 0);
+				for (uint32_t i = g.lane; i < nv; i += G)
+					t4[i] = z;
+			}
+			if (bulk) {
+				for (uint32_t i = n16 + g.lane; i < n; i += G)
+					sin[i] = src[i];
+				state = ST_LOADING;
+			} else {
+				load_block_to_smem<G>(g, sin, src, n);
+				state = ST_RUN;
+			}
+			g.sync();
 		}
-	} else {
-		const uint32_t total = gridDim.x * groups_per_cta;
-		for (uint32_t blk = blockIdx.x * groups_per_cta + gid; blk < p.a.n_blocks; blk += total)
-			compress_block<G>(g, p, blk, tab, sin, ring);
+		if (state == ST_LOADING) {
+			if (g.ballot(mbar_test(bar, parity)) != full)
+				continue;
+			parity ^= 1u;
+			state = ST_RUN;
+		}
+
+		// ---- one WINDOW of G probe positions (csnappy_compress.c:535-552 and 587-593) ----
+		// Lane k probes the k-th position of the window.  j0 + k is that probe's index in the
+		// reference's skip schedule (stride (32 + index) >> 5); lanes whose index is negative
+		// are the post-copy bookkeeping positions (t == 1: lane 0 = ip-1, insert only; lane 1 =
+		// ip, the re-probe) or lie before an in-window scan restart.  While every stride in the
+		// window is 1 ("uni") the window is G consecutive bytes and the parse can CONTINUE
+		// inside it after a copy: the lanes behind the copy already hold their hash, table
+		// entry and compare result, and those stay valid as long as no two lanes of the window
+		// share a hash slot.  That is checked by inserting speculatively and reading back;
+		// lanes that turn out not to insert (skipped by a copy, or behind the end) undo.
+		const bool uni = j0 <= 32 - G;
+		uint32_t pp, s;
+		if (uni) {
+			pp = wbase + g.lane;
+			s = 1;
+		} else {
+			const uint32_t s0 = (32u + j0) >> 5;
+			const int jb = ((j0 >> 5) + 1) << 5;  // first probe index with stride s0 + 1
+			pp = wbase + g.lane * s0 + max(j0 + (int)g.lane - jb, 0);
+			s = (32u + j0 + g.lane) >> 5;
+		}
+		const bool valid = pp + s <= ip_limit;
+		const uint32_t bytes = lds32u(sin, valid ? pp : 0u);
+		const uint32_t h = (bytes * kHashMul) >> shift;
+		const uint32_t old = tab[h];
+		g.sync();
+		if (valid)
+			tab[h] = (uint16_t)pp;
+		g.sync();
+		const bool exact = g.ballot(valid && tab[h] != pp) != 0;  // two lanes share a slot
+		// candidate: the table -- or, with shared slots, the latest lower lane with the same hash
+		// (invalid lanes must not follow a stale entry: blocks under 15 bytes never clear the table)
+		uint32_t cand = valid ? old : 0u;
+		unsigned same = 0;
+		if (exact) {
+			if (valid)
+				tab[h] = (uint16_t)old;	 // back to the state before this window
+			same = g.match(valid ? h : (0x80000000u | g.lane));
+			const unsigned lower = same & ((1u << g.lane) - 1u);
+			const uint32_t lp = g.bcast(pp, lower ? 31 - __clz(lower) : (int)g.lane);
+			if (lower)
+				cand = lp;
+			g.sync();
+		}
+		const uint32_t cb = lds32u(sin, cand);
+		const unsigned H = g.ballot(valid && cb == bytes);
+		const unsigned V = g.ballot(valid);
+		const bool multi = uni && !exact;
+
+		unsigned I = 0;	   // lanes whose insert stands
+		uint32_t ins = 0;  // first inserting lane of the current run
+		uint32_t cur = t;  // first lane that may hit
+		bool fin = false;
+		for (;;) {
+			const unsigned elig = H & (full << cur) & full;
+			if (!elig) {
+				I |= full << ins;
+				if (V != full) {
+					fin = true;  // ran into ip_limit without a hit
+				} else if (uni) {
+					wbase += G;
+					j0 += G;
+					t = 0;
+				} else {
+					const uint32_t s0 = (32u + j0) >> 5;
+					const int jb = ((j0 >> 5) + 1) << 5;
+					wbase += G * s0 + max(j0 + G - jb, 0);
+					j0 += G;
+					t = 0;
+				}
+				break;
+			}
+			const unsigned f = __ffs(elig) - 1;
+			I |= (full << ins) & ((2u << f) - 1u);
+			const uint32_t ip = g.bcast(pp, (int)f), cd = g.bcast(cand, (int)f);
+			// match extension, bounded by n (csnappy_compress.c:252-295): the first G bytes one
+			// byte per lane (most copies end there), then 4*G bytes per step
+			const uint32_t room = n - ip;
+			uint32_t m;
+			{
+				const unsigned ne = g.ballot(sin[cd + 4 + g.lane] != sin[ip + 4 + g.lane] || 4 + g.lane >= room);
+				m = 3 + __ffs(ne);
+				if (!ne) {
+					m = 4 + G;
+					for (;;) {
+						const uint32_t d = min(m + 4 * g.lane, room);
+						const uint32_t x = lds32u(sin, cd + d) ^ lds32u(sin, ip + d);
+						uint32_t mk = x ? d + ((uint32_t)(__ffs(x) - 1) >> 3) : 0x7fffffffu;
+						mk = g.min(min(mk, room));
+						if (mk < m + 4 * G) {
+							m = mk;
+							break;
+						}
+						m += 4 * G;
+					}
+				}
+			}
+			const uint32_t litlen = ip - next_emit;
+			if (m <= 64 && litlen <= (uint32_t)G - 4) {
+				// common case: literal (header + payload) and the copy tag leave in ONE store
+				uint32_t nb;
+				const uint32_t w = copy_piece(ip - cd, m, &nb);
+				const uint32_t lh = litlen ? litlen + 1 : 0;
+				const uint32_t lb = sin[next_emit + g.lane - 1];  // (lane 0 reads one byte below; unused)
+				uint32_t b = g.lane == 0 ? (litlen - 1) << 2 : lb;
+				if (g.lane >= lh)
+					b = w >> (8 * (g.lane - lh));
+				if (g.lane < lh + nb)
+					dst[op + g.lane] = (uint8_t)b;
+				op += lh + nb;
+			} else {
+				if (litlen)
+					op += emit_literal<G>(g, dst + op, sin, next_emit, litlen);
+				op += emit_copy<G>(g, dst + op, ip - cd, m);
+			}
+			next_emit = ip + m;
+			if (next_emit >= ip_limit) {
+				fin = true;
+				break;
+			}
+			const uint32_t nl = next_emit - wbase;	// lane of the re-probe position, if still inside
+			if (!multi || nl >= (uint32_t)G) {
+				wbase = next_emit - 1;
+				j0 = -2;
+				t = 1;
+				break;
+			}
+			// continue inside the window: lane nl-1 inserts ip-1, lane nl re-probes, scan restarts at nl+1
+			ins = nl - 1;
+			cur = nl;
+			j0 = -(int)(nl + 1);
+		}
+		if (!fin) {
+			const bool mine = (I >> g.lane) & 1u;
+			if (!exact) {
+				if (valid && !mine)
+					tab[h] = (uint16_t)old;	 // undo the speculative insert
+			} else {
+				// the highest inserting lane of an equal-hash run owns the slot
+				const unsigned rivals = same & I & ~((2u << g.lane) - 1u);
+				if (valid && mine && !rivals)
+					tab[h] = (uint16_t)pp;
+			}
+			g.sync();
+		} else {
+			if (next_emit < n)
+				op += emit_literal<G>(g, dst + op, sin, next_emit, n - next_emit);
+			if (g.lane == 0)
+				a.out_len[blk] = op;
+			state = ST_NEED;
+		}
 	}
 }
 
@@ -369,47 +415,48 @@ extern "C" int csb_launch_compress(const struct csb_compress_args *a, csb_stream
 	if (in_cap > CSB_FRAGMENT_MAX)
 		in_cap = CSB_FRAGMENT_MAX;
 	p.in_area = ((in_cap + 15u) & ~15u) + kInPad;
-	p.group_smem = p.table_bytes + p.in_area + kRing;
+	p.group_smem = p.table_bytes + p.in_area + 16;
 
-	const int G = a->lanes ? a->lanes : 32;
+	const int G = a->lanes ? a->lanes : 16;
 	const int ctas_per_sm = a->ctas_per_sm > 0 ? a->ctas_per_sm : 1;
 	// shared memory per CTA: the SM's carve-out divided among resident CTAs (1 KiB reserved each)
 	long budget = (long)di.smem_per_sm / ctas_per_sm - 1024;
 	if (budget > di.smem_per_block_optin)
 		budget = di.smem_per_block_optin;
 	int groups = (int)(budget / p.group_smem);
-	const int max_groups = 1024 / G;
+	const int max_groups = kMaxThreads / G;
 	if (groups > max_groups)
 		groups = max_groups;
 	if (groups < 1)
 		return (int)cudaErrorInvalidConfiguration;
+	long want = ((long)a->n_blocks + groups - 1) / groups;
+	long ctas = (long)di.sm_count * ctas_per_sm;
+	if (ctas > want) {
+		// small batch: spread the blocks over all SMs instead of filling a few CTAs
+		ctas = want;
+		if (a->n_blocks < (uint32_t)(di.sm_count * groups)) {
+			ctas = a->n_blocks < (uint32_t)di.sm_count ? (long)a->n_blocks : (long)di.sm_count;
+			groups = (int)(((long)a->n_blocks + ctas - 1) / ctas);
+		}
+	}
 	p.groups = (uint32_t)groups;
 	const int threads = (groups * G + 31) / 32 * 32;  // whole warps; surplus lanes exit at once
 	const size_t smem = (size_t)groups * p.group_smem;
 
-	long want = ((long)a->n_blocks + groups - 1) / groups;
-	long ctas = (long)di.sm_count * ctas_per_sm;
-	if (ctas > want)
-		ctas = want;
-
-	p.counter = nullptr;
 	uint32_t *counter = nullptr;
-	if ((long)a->n_blocks > ctas * groups) {
-		cudaError_t ce = cudaMallocAsync((void **)&counter, sizeof(uint32_t), s);
-		if (ce != cudaSuccess)
-			return (int)ce;
-		ce = cudaMemsetAsync(counter, 0, sizeof(uint32_t), s);
-		if (ce != cudaSuccess)
-			return (int)ce;
-		p.counter = counter;
-	}
+	cudaError_t ce = cudaMallocAsync((void **)&counter, sizeof(uint32_t), s);
+	if (ce != cudaSuccess)
+		return (int)ce;
+	ce = cudaMemsetAsync(counter, 0, sizeof(uint32_t), s);
+	if (ce != cudaSuccess)
+		return (int)ce;
+	p.counter = counter;
 	switch (G) {
 	case 32: e = launch_compress_g<32>(p, threads, (int)ctas, smem, s); break;
 	case 16: e = launch_compress_g<16>(p, threads, (int)ctas, smem, s); break;
 	case 8: e = launch_compress_g<8>(p, threads, (int)ctas, smem, s); break;
 	default: e = (int)cudaErrorInvalidValue; break;
 	}
-	if (counter)
-		cudaFreeAsync(counter, s);
+	cudaFreeAsync(counter, s);
 	return e;
 }

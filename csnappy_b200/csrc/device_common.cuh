@@ -31,7 +31,51 @@ struct Group {
 	template <typename T>
 	__device__ __forceinline__ T bcast(T v, int src) const { return __shfl_sync(mask, v, src, G); }
 	__device__ __forceinline__ unsigned match(unsigned key) const { return __match_any_sync(mask, key) >> shift; }
+	__device__ __forceinline__ unsigned min(unsigned v) const { return __reduce_min_sync(mask, v); }
+	__device__ __forceinline__ unsigned max(unsigned v) const { return __reduce_max_sync(mask, v); }
+	__device__ __forceinline__ unsigned add(unsigned v) const { return __reduce_add_sync(mask, v); }
 };
+
+// ---- shared-memory addresses, mbarrier and bulk async copy (TMA engine, SASS: UBLKCP) ----------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// orders earlier generic-proxy accesses to shared memory before later async-proxy (bulk copy) accesses
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// global -> shared bulk copy of `bytes` (multiple of 16; both addresses 16-byte aligned), completes on `bar`
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+		     "l"(src), "r"(bytes), "r"(bar)
+		     : "memory");
+}
+// shared -> global bulk copy (bulk async-group completion)
+__device__ __forceinline__ void bulk_s2g(void *dst, uint32_t src, uint32_t bytes)
+{
+	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes)
+		     : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the newest 0 bulk groups have finished READING their shared-memory source
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// non-blocking test of the phase with the given parity
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity)
+{
+	uint32_t ok;
+	asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+		     : "=r"(ok)
+		     : "r"(bar), "r"(parity)
+		     : "memory");
+	return ok != 0;
+}
 
 // little-endian 32-bit load at an arbitrary byte offset of a 4-byte aligned shared-memory area
 __device__ __forceinline__ uint32_t lds32u(const uint8_t *area, uint32_t off)

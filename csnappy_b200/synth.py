@@ -60,14 +60,16 @@ def page_classes(n_pages: int, seed: int, first_page: int = 0):
 
 
 def mixed_pages(n_pages: int, page_len: int = 4096, seed: int = 0x5EED0001, device="cuda", first_page: int = 0,
-                pool_bytes: int = 8 << 20, text_only: bool = False):
+                pool_bytes: int = 8 << 20, text_only: bool = False, only: str = ""):
     """uint8 tensor [n_pages * page_len] on `device` holding the zram-style mixed batch.
     `first_page` lets each rank of a sharded run generate exactly its slice of the global batch."""
     import torch
 
     cls, h = page_classes(n_pages, seed, first_page)
-    if text_only:
+    if text_only or only == "text":
         cls[:] = 0
+    elif only:
+        cls[:] = {"zero": 1, "random": 2}[only]
     pool = torch.from_numpy(text_pool(pool_bytes)).to(device)
     windows = pool.unfold(0, page_len, 1)  # [pool - page_len + 1, page_len] overlapping view
     pages = torch.zeros((n_pages, page_len), dtype=torch.uint8, device=device)
