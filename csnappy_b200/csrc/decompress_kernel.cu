@@ -6,19 +6,33 @@
 // (-5) before space (-3); end of input at a tag boundary is success -- or, with
 // CSNAPPY_BATCH_WITH_HEADER, of csnappy_decompress (csnappy_decompress.c:394-411).
 //
-// A GROUP of G lanes owns one block.  Two paths inside one kernel:
-//   staged     compressed block and output both fit the group's shared memory: the input is
-//              loaded with 16-byte coalesced loads, tags are interpreted against shared
-//              memory (back-references never touch HBM), the finished block is written to
-//              HBM with 16-byte coalesced stores.  This is the 4 KiB page / 32 KiB fragment path.
+// A GROUP of G lanes (8, 16 or 32) owns one block; a persistent CTA per SM holds as many groups
+// as shared memory allows (compressed block + output block: 24 x 4 KiB pages per SM).  Two paths:
+//
+//   staged     compressed block and output both fit the group's shared memory (4 KiB pages,
+//              32 KiB fragments).  The block arrives with one bulk async copy (UBLKCP, mbarrier
+//              completion).  The tag stream is decoded in BATCHES of G tags:
+//                walk     the only inherently serial part -- tag k+1 starts where tag k ends -- is
+//                         reduced to one byte load + one 256-entry table lookup per tag (the
+//                         reference's char_table idea, csnappy_decompress.c:139-185), executed
+//                         uniformly by the group; it also produces the output offset of every
+//                         tag (the prefix sum of lengths) and the length-type errors;
+//                decode   lane k decodes tag k completely (offset bytes, source, validity) --
+//                         G tags in parallel;
+//                execute  tags run in stream order, every lane moving bytes: literals and disjoint
+//                         copies G bytes per step, overlapping copies (offset < length) as a
+//                         pattern fill or in offset-sized rounds, all against shared memory.
+//              The finished block leaves with one bulk async store (shared -> global).
 //   streaming  anything larger (whole multi-chunk streams through the drop-in API): input and
-//              output stay in global memory, back-references are read through L2 (ld.cg).
+//              output stay in global memory, one tag at a time, back-references read through L2.
 #include "device_common.cuh"
 #include "kernels.h"
 
 namespace csb {
 
 constexpr int E_OK = 0, E_HEADER_BAD = -1, E_OUTPUT_INSUF = -2, E_OUTPUT_OVERRUN = -3, E_DATA_MALFORMED = -5;
+constexpr int kMaxThreadsD = 832;
+
 
 struct DecompressParams {
 	csb_decompress_args a;
@@ -29,19 +43,10 @@ struct DecompressParams {
 	uint32_t groups;  // groups per CTA that own shared memory
 };
 
-template <bool STAGED>
-__device__ __forceinline__ uint32_t load_out(const uint8_t *p)
-{
-	if (STAGED)
-		return *p;
-	return __ldcg(p);  // streaming path: written by other lanes of this group, read via L2
-}
-
-// Tag interpreter over ib[0..ilen) into ob[0..cap).  Every lane of the group walks the tags
-// redundantly (uniform control flow); payload bytes are moved G at a time.
-template <int G, bool STAGED>
-__device__ __forceinline__ int decode_core(const Group<G> &g, const uint8_t *ib, uint32_t ilen, uint8_t *ob,
-					   uint32_t cap, uint32_t *produced_out)
+// ---- streaming path: one tag at a time against global memory ---------------------------------
+template <int G>
+__device__ __forceinline__ int decode_streaming(const Group<G> &g, const uint8_t *ib, uint32_t ilen, uint8_t *ob,
+						uint32_t cap, uint32_t *produced_out)
 {
 	uint32_t pos = 0, produced = 0;
 	while (pos < ilen) {
@@ -92,22 +97,20 @@ __device__ __forceinline__ int decode_core(const Group<G> &g, const uint8_t *ib,
 			if (cap - produced < len)
 				return E_OUTPUT_OVERRUN;
 			const uint8_t *from = ob + produced - off;
+			// written by other lanes of this group: read through L2
 			if (off >= len) {
-				// disjoint: len <= 64, at most two rounds
 				for (uint32_t i = g.lane; i < len; i += G)
-					ob[produced + i] = load_out<STAGED>(from + i);
+					ob[produced + i] = __ldcg(from + i);
 			} else if (off >= (uint32_t)G) {
-				// overlapping but a round of G bytes only reads what earlier rounds wrote
 				for (uint32_t c = 0; c < len; c += G) {
 					const uint32_t i = c + g.lane;
 					if (i < len)
-						ob[produced + i] = load_out<STAGED>(from + i);
+						ob[produced + i] = __ldcg(from + i);
 					g.sync();
 				}
 			} else {
-				// short period: byte i repeats the pattern ob[produced-off .. produced)
 				for (uint32_t i = g.lane; i < len; i += G)
-					ob[produced + i] = load_out<STAGED>(from + (i % off));
+					ob[produced + i] = __ldcg(from + (i % off));
 			}
 		}
 		produced += len;
@@ -117,97 +120,335 @@ __device__ __forceinline__ int decode_core(const Group<G> &g, const uint8_t *ib,
 	return E_OK;
 }
 
+// ---- staged path: one batch of up to G tags ---------------------------------------------------
+struct StagedState {
+	uint32_t pos, produced;	 // input / output cursor
+	int irem, orem;		 // input bytes left, output capacity left
+};
+
+// Returns 1 when the stream is finished (rc says how), 0 to continue with the next batch.
+// gs = the group's shared memory; sin_off / sout_off = offsets of the staged input / output in it.
 template <int G>
-__device__ __forceinline__ void decompress_block(const Group<G> &g, const DecompressParams &p, uint32_t blk,
-						 uint8_t *sin, uint8_t *sout)
+__device__ __forceinline__ int decode_batch(const Group<G> &g, uint8_t *gs, uint32_t sin_off, uint32_t sout_off,
+					    const uint32_t *lut, uint32_t *meta, StagedState &st, int &rc)
 {
-	const csb_decompress_args &a = p.a;
-	const uint8_t *src = a.in + (a.in_off ? a.in_off[blk] : (uint64_t)blk * a.in_stride);
-	uint32_t ilen = a.in_len[blk];
-	uint32_t cap = a.out_cap ? a.out_cap[blk] : a.uniform_cap;
-	uint8_t *dst = a.out + (uint64_t)blk * a.out_stride;
-	int rc = E_OK;
-	uint32_t produced = 0;
-
-	if (a.flags & 2u) {  // varint32 length prefix, csnappy_decompress.c:45-71, 404-409
-		uint32_t shift = 0, used = 0, value = 0;
-		for (;;) {
-			if (shift >= 32 || used == ilen) {
-				rc = E_HEADER_BAD;
-				break;
-			}
-			const uint32_t c = src[used++];
-			value |= (c & 0x7fu) << shift;
-			if (c < 128)
-				break;
-			shift += 7;
-		}
-		if (rc == E_OK) {
-			if (value > cap)
-				rc = E_OUTPUT_INSUF;
-			cap = value;
-			src += used;
-			ilen -= used;
-		}
+	const uint8_t *sin = gs + sin_off;
+	uint32_t pos = st.pos, produced = st.produced;
+	int irem = st.irem, orem = st.orem;
+	// ---- walk: positions and output offsets of up to G tags; ONE exit test per tag ----
+	// lut[tag] = input bytes of the whole tag | output bytes << 16; a long literal has 0xffff input
+	// bytes, so "input exhausted", "long literal", "payload cut off" and "no space" all show up as a
+	// negative remainder and are told apart once, after the loop.
+	uint32_t k = 0, e = 0;
+#pragma unroll 4
+	for (; k < (uint32_t)G; ++k) {
+		e = lut[sin[pos]];
+		meta[k] = pos | (produced << 16);
+		const int x = irem - (int)(e & 0xffffu), y = orem - (int)(e >> 16);
+		if ((x | y) < 0)
+			break;
+		pos += e & 0xffffu;
+		produced += e >> 16;
+		irem = x;
+		orem = y;
 	}
+	const uint32_t ntags = k;  // complete tags of this batch
+	int werr = E_OK;
+	bool stop = false, longlit = false;
+	if (k < (uint32_t)G) {
+		if (irem == 0)
+			stop = true;  // end of input at a tag boundary
+		else if ((e & 0xffffu) == 0xffffu)
+			longlit = true;
+		else if (irem < (int)(e & 0xffffu))
+			werr = E_DATA_MALFORMED;  // literal payload or copy offset bytes cut off by end of input
+		else
+			werr = E_OUTPUT_OVERRUN;  // (a copy still has its offset validated first, below)
+	}
+	g.sync();
 
-	if (rc == E_OK) {
-		if (ilen <= p.in_area && cap <= p.out_area) {
-			g.sync();  // previous block's readers of the staging areas are done
-			load_block_to_smem<G>(g, sin, src, ilen);
-			g.sync();
-			rc = decode_core<G, true>(g, sin, ilen, sout, cap, &produced);
-			if (rc == E_OK) {
-				if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
-					const uint32_t nv = produced >> 4;
-					const uint4 *s4 = reinterpret_cast<const uint4 *>(sout);
-					uint4 *d4 = reinterpret_cast<uint4 *>(dst);
-					for (uint32_t i = g.lane; i < nv; i += G)
-						stg_stream(d4 + i, s4[i]);
-					for (uint32_t i = (nv << 4) + g.lane; i < produced; i += G)
-						dst[i] = sout[i];
-				} else {
-					for (uint32_t i = g.lane; i < produced; i += G)
-						dst[i] = sout[i];
-				}
-			}
+	// ---- decode: lane k owns tag k (plus the tag that ran out of space: offset check only) ----
+	uint32_t d0 = 0, d1 = 0;
+	bool bad = false;
+	if (g.lane < ntags + (werr == E_OUTPUT_OVERRUN ? 1u : 0u)) {
+		const uint32_t mp = meta[g.lane];
+		const uint32_t p = mp & 0xffffu, o = mp >> 16;
+		const uint32_t tag = sin[p];
+		const uint32_t kind = tag & 3u;
+		uint32_t len = (tag >> 2) + 1;
+		d1 = sout_off + o;
+		if (kind == 0) {
+			d0 = (sin_off + p + 1) | (len << 20);  // literal: source is the input
 		} else {
-			rc = decode_core<G, false>(g, src, ilen, dst, cap, &produced);
+			uint32_t off = sin[p + 1];
+			if (kind == 1) {
+				len = ((tag >> 2) & 7u) + 4;
+				off |= (tag >> 5) << 8;
+			} else {
+				off |= (uint32_t)sin[p + 2] << 8;
+				if (kind == 3)
+					off |= ((uint32_t)sin[p + 3] << 16) | ((uint32_t)sin[p + 4] << 24);
+			}
+			bad = off - 1u >= o;  // off == 0 or off > produced, csnappy_decompress.c:302
+			d0 = ((d1 - off) & 0xfffffu) | (len << 20);
+			if (off < len) {  // overlapping: mode bit + the period
+				d0 |= 1u << 28;
+				d1 |= off << 20;
+			}
 		}
 	}
-	if (g.lane == 0) {
-		a.status[blk] = rc;
-		a.out_len[blk] = rc == E_OK ? produced : 0u;
+	const unsigned badmask = g.ballot(bad);
+	if (badmask || werr != E_OK) {
+		// first failing tag in stream order: an invalid offset at or before the walk's failing tag wins
+		rc = badmask ? E_DATA_MALFORMED : werr;
+		return 1;
 	}
+	uint2 *desc = reinterpret_cast<uint2 *>(meta + G);
+	desc[g.lane] = make_uint2(d0, d1);
+	g.sync();
+
+	// ---- execute in stream order, all lanes moving bytes ----
+	for (uint32_t t = 0; t < ntags; ++t) {
+		const uint2 d = desc[t];
+		const uint8_t *from = gs + (d.x & 0xfffffu);
+		uint8_t *to = gs + (d.y & 0xfffffu);
+		const uint32_t len = (d.x >> 20) & 0xffu;
+		if (!(d.x >> 28)) {
+			// literal or disjoint copy (len <= 64)
+			for (uint32_t i = g.lane; i < len; i += G)
+				to[i] = from[i];
+		} else {
+			const uint32_t off = d.y >> 20;
+			if (off == 1) {
+				const uint8_t v = from[0];
+				for (uint32_t i = g.lane; i < len; i += G)
+					to[i] = v;
+			} else if (off >= (uint32_t)G) {
+				// a round of G bytes only reads what earlier rounds wrote
+				for (uint32_t c = 0; c < len; c += G) {
+					const uint32_t i = c + g.lane;
+					if (i < len)
+						to[i] = from[i];
+					g.sync();
+				}
+			} else {
+				// short period: byte i repeats the pattern [o - off, o)
+				for (uint32_t i = g.lane; i < len; i += G)
+					to[i] = from[i % off];
+			}
+		}
+		g.sync();
+	}
+
+	// ---- a long literal (61+ bytes, 1-4 length bytes) ends the batch and is copied by all lanes ----
+	if (longlit) {
+		const uint32_t ilen = pos + (uint32_t)irem;
+		const uint32_t tag = sin[pos++];
+		const uint32_t nb = (tag >> 2) + 1 - 60;
+		if (ilen - pos < nb) {
+			rc = E_DATA_MALFORMED;
+			return 1;
+		}
+		uint32_t v = 0;
+		for (uint32_t b = 0; b < nb; ++b)
+			v |= (uint32_t)sin[pos + b] << (8 * b);
+		pos += nb;
+		const uint32_t len = v + 1;  // 0xffffffff wraps to a zero-length literal (csnappy_decompress.c:370)
+		// (a length of 2^31 or more passes the reference's signed input check and fails on space, :374)
+		if ((int32_t)len >= 0 && ilen - pos < len) {
+			rc = E_DATA_MALFORMED;
+			return 1;
+		}
+		if ((uint32_t)orem < len) {
+			rc = E_OUTPUT_OVERRUN;
+			return 1;
+		}
+		uint8_t *to = gs + sout_off + produced;
+		const uint32_t head = min((uint32_t)(-(intptr_t)to) & 3u, len);
+		if (g.lane < head)
+			to[g.lane] = sin[pos + g.lane];
+		const uint32_t words = (len - head) >> 2;
+		uint32_t *tw = reinterpret_cast<uint32_t *>(to + head);
+		for (uint32_t w = g.lane; w < words; w += G)
+			tw[w] = lds32u(sin, pos + head + 4 * w);
+		const uint32_t tail = head + (words << 2);
+		if (tail + g.lane < len)
+			to[tail + g.lane] = sin[pos + tail + g.lane];
+		pos += len;
+		produced += len;
+		irem = (int)(ilen - pos);
+		orem -= (int)len;
+		g.sync();
+	}
+	st.pos = pos;
+	st.produced = produced;
+	st.irem = irem;
+	st.orem = orem;
+	if (stop) {
+		rc = E_OK;
+		return 1;
+	}
+	return 0;
 }
 
+enum : int { DS_NEED = 0, DS_LOADING = 1, DS_RUN = 2 };
+
 template <int G>
-__global__ void __launch_bounds__(1024) decompress_kernel(const DecompressParams p)
+__global__ void __launch_bounds__(kMaxThreadsD) decompress_kernel(const DecompressParams p)
 {
-	extern __shared__ __align__(16) uint8_t smem[];
+	extern __shared__ __align__(128) uint8_t smem[];
+	__shared__ uint32_t lut[256];
+	// walk table (csnappy_decompress.c:139-185 restated): input bytes of the whole tag | output bytes << 16
+	for (uint32_t t = threadIdx.x; t < 256; t += blockDim.x) {
+		const uint32_t kind = t & 3u, l = (t >> 2) + 1;
+		uint32_t e;
+		if (kind == 0)
+			e = l > 60 ? 0xffffu : ((1 + l) | (l << 16));
+		else if (kind == 1)
+			e = 2u | ((((t >> 2) & 7u) + 4) << 16);
+		else
+			e = (kind == 2 ? 3u : 5u) | (l << 16);
+		lut[t] = e;
+	}
+	__syncthreads();
+
 	const Group<G> g;
-	const uint32_t groups_per_cta = p.groups;
 	const uint32_t gid = threadIdx.x / G;
 	if (gid >= p.groups)
-		return;	 // padding lanes of the last warp (no block-wide barriers in this kernel)
-	uint8_t *sin = smem + (size_t)gid * p.group_smem;
+		return;	 // padding lanes of the last warp (no block-wide barriers below)
+	const csb_decompress_args &a = p.a;
+	uint8_t *gs = smem + (size_t)gid * p.group_smem;
+	uint8_t *sin = gs;
 	uint8_t *sout = sin + p.in_area;
+	uint32_t *meta = reinterpret_cast<uint32_t *>(sout + p.out_area);  // G walk words + G descriptors
+	const uint32_t bar = smem_u32(meta + 3 * G);
+	const unsigned full = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
 
-	if (p.counter) {
-		for (;;) {
-			uint32_t blk = 0;
+	if (g.lane == 0) {
+		mbar_init(bar, 1);
+		fence_mbar_init();
+	}
+	g.sync();
+
+	int state = DS_NEED;
+	uint32_t parity = 0, blk = 0;
+	StagedState st = {0, 0, 0, 0};
+	uint8_t *dst = nullptr;
+
+	for (;;) {
+		if (state == DS_NEED) {
 			if (g.lane == 0)
 				blk = atomicAdd(p.counter, 1u);
 			blk = g.bcast(blk, 0);
-			if (blk >= p.a.n_blocks)
+			if (blk >= a.n_blocks)
 				break;
-			decompress_block<G>(g, p, blk, sin, sout);
+			const uint8_t *src = a.in + (a.in_off ? a.in_off[blk] : (uint64_t)blk * a.in_stride);
+			uint32_t ilen = a.in_len[blk];
+			uint32_t cap = a.out_cap ? a.out_cap[blk] : a.uniform_cap;
+			dst = a.out + (uint64_t)blk * a.out_stride;
+			int rc = E_OK;
+			if (a.flags & 2u) {  // varint32 length prefix, csnappy_decompress.c:45-71, 404-409
+				uint32_t shift = 0, used = 0, value = 0;
+				for (;;) {
+					if (shift >= 32 || used == ilen) {
+						rc = E_HEADER_BAD;
+						break;
+					}
+					const uint32_t c = src[used++];
+					value |= (c & 0x7fu) << shift;
+					if (c < 128)
+						break;
+					shift += 7;
+				}
+				if (rc == E_OK) {
+					if (value > cap)
+						rc = E_OUTPUT_INSUF;
+					cap = value;
+					src += used;
+					ilen -= used;
+				}
+			}
+			if (rc == E_OK && !(ilen + 16 <= p.in_area && cap <= p.out_area)) {
+				uint32_t produced = 0;
+				rc = decode_streaming<G>(g, src, ilen, dst, cap, &produced);
+				if (g.lane == 0) {
+					a.status[blk] = rc;
+					a.out_len[blk] = rc == E_OK ? produced : 0u;
+				}
+				continue;
+			}
+			if (rc != E_OK) {
+				if (g.lane == 0) {
+					a.status[blk] = rc;
+					a.out_len[blk] = 0u;
+				}
+				continue;
+			}
+			// staged: the previous block's output store must have finished reading shared memory
+			if (g.lane == 0)
+				bulk_wait_read0();
+			g.sync();
+			st.pos = 0;
+			st.produced = 0;
+			st.irem = (int)ilen;
+			st.orem = (int)cap;
+			const bool bulk = (reinterpret_cast<uintptr_t>(src) & 15u) == 0 && ilen >= 16;
+			const uint32_t n16 = bulk ? (ilen & ~15u) : 0;
+			if (bulk) {
+				if (g.lane == 0) {
+					fence_proxy_async();
+					mbar_expect_tx(bar, n16);
+					bulk_g2s(smem_u32(sin), src, n16, bar);
+				}
+				for (uint32_t i = n16 + g.lane; i < ilen; i += G)
+					sin[i] = src[i];
+				state = DS_LOADING;
+			} else {
+				load_block_to_smem<G>(g, sin, src, ilen);
+				state = DS_RUN;
+			}
+			g.sync();
 		}
-	} else {
-		const uint32_t total = gridDim.x * groups_per_cta;
-		for (uint32_t blk = blockIdx.x * groups_per_cta + gid; blk < p.a.n_blocks; blk += total)
-			decompress_block<G>(g, p, blk, sin, sout);
+		if (state == DS_LOADING) {
+			if (g.ballot(mbar_test(bar, parity)) != full)
+				continue;
+			parity ^= 1u;
+			state = DS_RUN;
+		}
+
+		int rc = E_OK;
+		if (!decode_batch<G>(g, gs, 0u, p.in_area, lut, meta, st, rc))
+			continue;
+
+		// ---- block finished ----
+		const uint32_t produced = st.produced;
+		if (rc == E_OK) {
+			if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+				const uint32_t n16 = produced & ~15u;
+				if (n16) {
+					fence_proxy_async();  // this lane's generic writes to sout -> async proxy
+					g.sync();
+					if (g.lane == 0) {
+						bulk_s2g(dst, smem_u32(sout), n16);
+						bulk_commit();
+					}
+				}
+				for (uint32_t i = n16 + g.lane; i < produced; i += G)
+					dst[i] = sout[i];
+			} else {
+				for (uint32_t i = g.lane; i < produced; i += G)
+					dst[i] = sout[i];
+			}
+		}
+		if (g.lane == 0) {
+			a.status[blk] = rc;
+			a.out_len[blk] = rc == E_OK ? produced : 0u;
+		}
+		state = DS_NEED;
 	}
+	// outstanding bulk stores read shared memory: they must finish before the CTA's memory is released
+	if (g.lane == 0)
+		bulk_wait_read0();
 }
 
 }  // namespace csb
@@ -236,6 +477,7 @@ extern "C" int csb_launch_decompress(const struct csb_decompress_args *a, csb_st
 
 	DecompressParams p;
 	p.a = *a;
+	const int G = a->lanes ? a->lanes : 16;
 	// staging capacities: output from the (uniform) capacity or the stride, input from the hint,
 	// the stride, or the format's worst case for that output size; both capped at fragment scale
 	uint64_t out_cap = a->out_cap ? a->out_stride : a->uniform_cap;
@@ -249,54 +491,52 @@ extern "C" int csb_launch_decompress(const struct csb_decompress_args *a, csb_st
 	}
 	if (in_cap > 32 + CSB_FRAGMENT_MAX + CSB_FRAGMENT_MAX / 6)
 		in_cap = 32 + CSB_FRAGMENT_MAX + CSB_FRAGMENT_MAX / 6;
-	p.in_area = (uint32_t)((in_cap + 15) & ~15ull);
+	p.in_area = (uint32_t)((in_cap + 15) & ~15ull) + 16;  // + slack for 4-byte over-reads of a literal source
 	p.out_area = (uint32_t)((out_cap + 15) & ~15ull);
-	p.group_smem = p.in_area + p.out_area;
-	if (p.group_smem == 0)
-		p.group_smem = 16;
+	const uint32_t meta_bytes = 12u * (uint32_t)G + 16u;  // walk words, descriptors, mbarrier
+	p.group_smem = p.in_area + p.out_area + meta_bytes;
 
-	const int G = a->lanes ? a->lanes : 32;
 	const int ctas_per_sm = a->ctas_per_sm > 0 ? a->ctas_per_sm : 1;
-	long budget = (long)di.smem_per_sm / ctas_per_sm - 1024;
-	if (budget > di.smem_per_block_optin)
-		budget = di.smem_per_block_optin;
+	long budget = (long)di.smem_per_sm / ctas_per_sm - 1024 - 1024;  // 1024: the static walk table
+	if (budget > di.smem_per_block_optin - 1024)
+		budget = di.smem_per_block_optin - 1024;
 	int groups = (int)(budget / p.group_smem);
-	const int max_groups = 1024 / G;
+	const int max_groups = kMaxThreadsD / G;
 	if (groups > max_groups)
 		groups = max_groups;
 	if (groups < 1) {
 		// cannot stage even one block: run streaming only
 		p.in_area = p.out_area = 0;
-		p.group_smem = 16;
+		p.group_smem = meta_bytes;
 		groups = 256 / G;
+	}
+	long want = ((long)a->n_blocks + groups - 1) / groups;
+	long ctas = (long)di.sm_count * ctas_per_sm;
+	if (ctas > want) {
+		ctas = want;
+		if (a->n_blocks < (uint32_t)(di.sm_count * groups)) {
+			ctas = a->n_blocks < (uint32_t)di.sm_count ? (long)a->n_blocks : (long)di.sm_count;
+			groups = (int)(((long)a->n_blocks + ctas - 1) / ctas);
+		}
 	}
 	p.groups = (uint32_t)groups;
 	const int threads = (groups * G + 31) / 32 * 32;  // whole warps; surplus lanes exit at once
 	const size_t smem = (size_t)groups * p.group_smem;
 
-	long want = ((long)a->n_blocks + groups - 1) / groups;
-	long ctas = (long)di.sm_count * ctas_per_sm;
-	if (ctas > want)
-		ctas = want;
-
-	p.counter = nullptr;
 	uint32_t *counter = nullptr;
-	if ((long)a->n_blocks > ctas * groups) {
-		cudaError_t ce = cudaMallocAsync((void **)&counter, sizeof(uint32_t), s);
-		if (ce != cudaSuccess)
-			return (int)ce;
-		ce = cudaMemsetAsync(counter, 0, sizeof(uint32_t), s);
-		if (ce != cudaSuccess)
-			return (int)ce;
-		p.counter = counter;
-	}
+	cudaError_t ce = cudaMallocAsync((void **)&counter, sizeof(uint32_t), s);
+	if (ce != cudaSuccess)
+		return (int)ce;
+	ce = cudaMemsetAsync(counter, 0, sizeof(uint32_t), s);
+	if (ce != cudaSuccess)
+		return (int)ce;
+	p.counter = counter;
 	switch (G) {
 	case 32: e = launch_decompress_g<32>(p, threads, (int)ctas, smem, s); break;
 	case 16: e = launch_decompress_g<16>(p, threads, (int)ctas, smem, s); break;
 	case 8: e = launch_decompress_g<8>(p, threads, (int)ctas, smem, s); break;
 	default: e = (int)cudaErrorInvalidValue; break;
 	}
-	if (counter)
-		cudaFreeAsync(counter, s);
+	cudaFreeAsync(counter, s);
 	return e;
 }
