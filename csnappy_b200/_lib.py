@@ -32,6 +32,9 @@ def _declare(L):
         "csnappy_batch_pack": (i, [vp, u64, vp, u32, vp, vp, vp]),
         "csnappy_batch_compress_fragments_host": (i, [vp, u64, u32, u32, vp, u64, vp, i]),
         "csnappy_batch_decompress_host": (i, [vp, u64, vp, u32, vp, u64, u32, vp, vp, u32]),
+        "csnappy_bc_max_container_length": (u64, [u64, u32]),
+        "csnappy_bc_compress_host": (i, [vp, u64, u32, vp, u64, C.POINTER(C.c_uint64), i]),
+        "csnappy_bc_decompress_host": (i, [vp, u64, u32, vp, u64, C.POINTER(C.c_uint64), _u32p]),
         "csnappy_b200_device_ok": (i, []),
         "csnappy_b200_last_error": (C.c_char_p, []),
         "csnappy_b200_kernel_launches": (u64, []),

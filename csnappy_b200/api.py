@@ -34,6 +34,7 @@ CSNAPPY_E_DEVICE = -100
 CSNAPPY_E_BAD_ARG = -101
 BATCH_SHRINK_TABLE = 1
 BATCH_WITH_HEADER = 2
+BATCH_RAW_IF_FULL = 4
 FRAGMENT_MAX = 32768
 
 
@@ -195,6 +196,34 @@ def batch_decompress_host(h_in, in_stride: int, h_in_len, n_blocks: int, h_out, 
                                               _host_ptr(h_out), out_stride, out_cap, _host_ptr(h_out_len),
                                               _host_ptr(h_status), flags)
     _check(rc, "csnappy_batch_decompress_host")
+
+
+# ----------------------------------------------------------------------------- block_compressor container
+def bc_max_container_length(input_length: int, page_size: int = 4096) -> int:
+    return lib().csnappy_bc_max_container_length(input_length, page_size)
+
+
+def bc_compress_host(h_in, input_length: int, h_container, wm: int = 13, page_size: int = 4096) -> int:
+    """block_compressor-style container of `input_length` bytes at h_in (numpy / pinned torch) into
+    h_container; returns the container length.  Reference: block_compressor.c:275-345."""
+    clen = C.c_uint64(0)
+    cap = h_container.nbytes if isinstance(h_container, np.ndarray) else h_container.numel() * h_container.element_size()
+    rc = lib().csnappy_bc_compress_host(_host_ptr(h_in), input_length, page_size, _host_ptr(h_container), cap,
+                                        C.byref(clen), wm)
+    _check(rc, "csnappy_bc_compress_host")
+    return clen.value
+
+
+def bc_decompress_host(h_container, container_length: int, h_out, page_size: int = 4096):
+    """-> (rc, bytes produced, failed page or None).  Reference: block_compressor.c:347-394."""
+    olen = C.c_uint64(0)
+    bad = C.c_uint32(0xFFFFFFFF)
+    cap = h_out.nbytes if isinstance(h_out, np.ndarray) else h_out.numel() * h_out.element_size()
+    rc = lib().csnappy_bc_decompress_host(_host_ptr(h_container), container_length, page_size, _host_ptr(h_out), cap,
+                                          C.byref(olen), C.byref(bad))
+    if rc in (CSNAPPY_E_DEVICE, CSNAPPY_E_BAD_ARG):
+        _check(rc, "csnappy_bc_decompress_host")
+    return rc, olen.value, (bad.value if rc != 0 and bad.value != 0xFFFFFFFF else None)
 
 
 def set_tuning(key: str, value: int):

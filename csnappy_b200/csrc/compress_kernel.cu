@@ -31,7 +31,7 @@
 
 namespace csb {
 
-constexpr uint32_t kInPad = 32;	     // slack after the staged input for 4-byte over-reads
+constexpr uint32_t kInPad = 48;	     // staging shift (< 16) + slack after the input for over-reads of the match extension
 constexpr uint32_t kTailMargin = 15; // kInputMarginBytes, csnappy_compress.c:468
 constexpr int kMaxThreads = 640;
 
@@ -146,8 +146,9 @@ __global__ void __launch_bounds__(kMaxThreads) compress_kernel(const CompressPar
 	const csb_compress_args &a = p.a;
 	uint8_t *gs = smem + (size_t)gid * p.group_smem;
 	uint16_t *tab = reinterpret_cast<uint16_t *>(gs);
-	uint8_t *sin = gs + p.table_bytes;
-	const uint32_t bar = smem_u32(sin + p.in_area);
+	uint8_t *sarea = gs + p.table_bytes;  // staged input, 16-byte aligned
+	const uint8_t *sin = sarea;	      // + (src & 15): where the block's first byte lands
+	const uint32_t bar = smem_u32(sarea + p.in_area);
 	const unsigned full = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
 
 	if (g.lane == 0) {
@@ -197,13 +198,6 @@ __global__ void __launch_bounds__(kMaxThreads) compress_kernel(const CompressPar
 			t = 0;
 
 			g.sync();  // every lane is done with the previous block's input and table
-			const bool bulk = (reinterpret_cast<uintptr_t>(src) & 15u) == 0 && n >= 16;
-			const uint32_t n16 = bulk ? (n & ~15u) : 0;
-			if (bulk && g.lane == 0) {
-				fence_proxy_async();  // generic-proxy reads of sin precede the async-proxy write
-				mbar_expect_tx(bar, n16);
-				bulk_g2s(smem_u32(sin), src, n16, bar);
-			}
 			if (n >= kTailMargin) {	 // zero the table, csnappy_compress.c:501
 				uint4 *t4 = reinterpret_cast<uint4 *>(tab);
 				const uint32_t nv = (1u << ws) >> 4;
@@ -211,14 +205,9 @@ __global__ void __launch_bounds__(kMaxThreads) compress_kernel(const CompressPar
 				for (uint32_t i = g.lane; i < nv; i += G)
 					t4[i] = z;
 			}
-			if (bulk) {
-				for (uint32_t i = n16 + g.lane; i < n; i += G)
-					sin[i] = src[i];
-				state = ST_LOADING;
-			} else {
-				load_block_to_smem<G>(g, sin, src, n);
-				state = ST_RUN;
-			}
+			bool bulk;
+			sin = sarea + stage_block<G>(g, sarea, src, n, bar, &bulk);
+			state = bulk ? ST_LOADING : ST_RUN;
 			g.sync();
 		}
 		if (state == ST_LOADING) {
@@ -417,7 +406,7 @@ extern "C" int csb_launch_compress(const struct csb_compress_args *a, csb_stream
 	p.in_area = ((in_cap + 15u) & ~15u) + kInPad;
 	p.group_smem = p.table_bytes + p.in_area + 16;
 
-	const int G = a->lanes ? a->lanes : 16;
+	const int G = a->lanes ? a->lanes : 32;
 	const int ctas_per_sm = a->ctas_per_sm > 0 ? a->ctas_per_sm : 1;
 	// shared memory per CTA: the SM's carve-out divided among resident CTAs (1 KiB reserved each)
 	long budget = (long)di.smem_per_sm / ctas_per_sm - 1024;

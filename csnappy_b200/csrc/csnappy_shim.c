@@ -543,3 +543,276 @@ out:
 	pthread_mutex_unlock(&C.mu);
 	return rc;
 }
+
+/* ---- block_compressor-style container on host buffers ----------------------------------
+ * Layout (reference block_compressor.c:275-394):
+ *     [u32 nr_pages][u32 clen[nr_pages]][payload_0]...[payload_{nr_pages-1}]
+ * payload_i is csnappy_compress_fragment(page_i, wm) or, when that is not smaller than the
+ * page, the page itself with clen_i = its length (:316-318); the reader treats
+ * clen_i == page_size as stored (:378).  Pages are compressed, size-scanned and packed on the
+ * device chunk by chunk; four chunks are in flight so that H2D, kernels and D2H overlap, and
+ * only COMPRESSED bytes cross the bus on the compressed side.
+ */
+#define BC_PIPE 4
+
+struct bc_slot {
+	cudaStream_t s;
+	cudaEvent_t ev;
+	struct buf d_in, d_slots, d_len, d_clen, d_off, d_packed, d_out, d_res;
+	struct buf h_res; /* pinned: [u64 total] or [u32 out_len[n]][i32 status[n]] */
+	int busy;
+	uint64_t first;
+	uint32_t n;
+};
+static struct bc_slot BC[BC_PIPE];
+static int bc_ready;
+
+static int bc_init(void)
+{
+	int i, e;
+	if (bc_ready)
+		return 0;
+	for (i = 0; i < BC_PIPE; i++) {
+		if ((e = (int)cudaStreamCreateWithFlags(&BC[i].s, cudaStreamNonBlocking)))
+			return e;
+		if ((e = (int)cudaEventCreateWithFlags(&BC[i].ev, cudaEventDisableTiming)))
+			return e;
+	}
+	bc_ready = 1;
+	return 0;
+}
+
+static uint32_t bc_chunk_pages(uint32_t page_size, uint64_t nr_pages)
+{
+	uint64_t pages = (32ull << 20) / page_size;
+	if (pages < 256)
+		pages = 256;
+	if (pages > nr_pages)
+		pages = nr_pages;
+	return (uint32_t)pages;
+}
+
+uint64_t csnappy_bc_max_container_length(uint64_t input_length, uint32_t page_size)
+{
+	uint64_t nr = page_size ? (input_length + page_size - 1) / page_size : 0;
+	return 4 + 4 * nr + input_length;
+}
+
+int csnappy_bc_compress_host(const void *h_in, uint64_t input_length, uint32_t page_size, void *h_container,
+			     uint64_t container_capacity, uint64_t *container_length,
+			     int workmem_bytes_power_of_two)
+{
+	int rc = 0, k;
+	uint64_t nr, done, payload_pos, retire_next = 0, issued = 0;
+	uint32_t chunk, out_stride;
+	uint8_t *cont = (uint8_t *)h_container;
+	if (workmem_bytes_power_of_two < 9 || workmem_bytes_power_of_two > 16)
+		return set_err("workmem_bytes_power_of_two outside 9..16", 0);
+	if (page_size == 0 || page_size > CSB_FRAGMENT_MAX)
+		return set_err("page_size outside 1..32768", 0);
+	nr = (input_length + page_size - 1) / page_size;
+	if (nr > 0xffffffffull)
+		return set_err("input too big", 0);
+	if (!h_container || !container_length || (input_length && !h_in) ||
+	    container_capacity < csnappy_bc_max_container_length(input_length, page_size))
+		return set_err("container buffer missing or smaller than csnappy_bc_max_container_length", 0);
+	{
+		uint32_t nr32 = (uint32_t)nr;
+		memcpy(cont, &nr32, 4);
+	}
+	payload_pos = 4 + 4 * nr;
+	*container_length = payload_pos;
+	if (nr == 0)
+		return 0;
+	chunk = bc_chunk_pages(page_size, nr);
+	out_stride = (csnappy_max_compressed_length(page_size) + 15u) & ~15u;
+
+	pthread_mutex_lock(&C.mu);
+	TRY("stream create", bc_init());
+	for (k = 0; k < BC_PIPE; k++) {
+		struct bc_slot *b = &BC[k];
+		TRY("cudaMalloc(in)", grow_dev(&b->d_in, (size_t)chunk * page_size + 64));
+		TRY("cudaMalloc(slots)", grow_dev(&b->d_slots, (size_t)chunk * out_stride + 64));
+		TRY("cudaMalloc(len)", grow_dev(&b->d_len, (size_t)chunk * 4 + 64));
+		TRY("cudaMalloc(clen)", grow_dev(&b->d_clen, (size_t)chunk * 4 + 64));
+		TRY("cudaMalloc(off)", grow_dev(&b->d_off, ((size_t)chunk + 1) * 8 + 64));
+		TRY("cudaMalloc(packed)", grow_dev(&b->d_packed, (size_t)chunk * page_size + 64));
+		TRY("cudaMallocHost(res)", grow_pin(&b->h_res, 64));
+		b->busy = 0;
+	}
+	for (done = 0; done < nr || retire_next < issued;) {
+		/* retire the oldest chunk once two younger ones are queued (or nothing is left to queue) */
+		if (retire_next < issued && (issued - retire_next > 2 || done >= nr)) {
+			struct bc_slot *b = &BC[retire_next % BC_PIPE];
+			uint64_t total;
+			TRY("event sync", cudaEventSynchronize(b->ev));
+			total = *(uint64_t *)b->h_res.p;
+			TRY("D2H payload", cudaMemcpyAsync(cont + payload_pos, b->d_packed.p, total, cudaMemcpyDeviceToHost, b->s));
+			payload_pos += total;
+			retire_next++;
+			continue;
+		}
+		{
+			struct bc_slot *b = &BC[issued % BC_PIPE];
+			uint64_t left_pages = nr - done, in_at = done * page_size;
+			uint32_t nb = left_pages < chunk ? (uint32_t)left_pages : chunk;
+			uint64_t in_bytes = input_length - in_at < (uint64_t)nb * page_size ? input_length - in_at
+											      : (uint64_t)nb * page_size;
+			struct csb_compress_args a;
+			TRY("H2D", cudaMemcpyAsync(b->d_in.p, (const uint8_t *)h_in + in_at, in_bytes, cudaMemcpyHostToDevice, b->s));
+			memset(&a, 0, sizeof(a));
+			a.in = (const uint8_t *)b->d_in.p;
+			a.in_stride = page_size;
+			a.uniform_len = page_size;
+			a.total_len = in_bytes;
+			a.n_blocks = nb;
+			a.out = (uint8_t *)b->d_slots.p;
+			a.out_stride = out_stride;
+			a.out_len = (uint32_t *)b->d_len.p;
+			a.wm = workmem_bytes_power_of_two;
+			a.lanes = g_compress_lanes;
+			a.ctas_per_sm = g_ctas_per_sm;
+			TRY("compress launch", csb_launch_compress(&a, (csb_stream_t)b->s));
+			TRY("pack launch", csb_launch_pack_stored((const uint8_t *)b->d_slots.p, out_stride, (const uint32_t *)b->d_len.p, nb,
+								  (const uint8_t *)b->d_in.p, page_size, in_bytes, (uint32_t *)b->d_clen.p,
+								  (uint8_t *)b->d_packed.p, (uint64_t *)b->d_off.p, (csb_stream_t)b->s));
+			TRY("D2H total", cudaMemcpyAsync(b->h_res.p, (uint64_t *)b->d_off.p + nb, 8, cudaMemcpyDeviceToHost, b->s));
+			TRY("D2H index", cudaMemcpyAsync(cont + 4 + 4 * done, b->d_clen.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, b->s));
+			TRY("event record", cudaEventRecord(b->ev, b->s));
+			done += nb;
+			issued++;
+		}
+	}
+	for (k = 0; k < BC_PIPE; k++)
+		TRY("sync", cudaStreamSynchronize(BC[k].s));
+	*container_length = payload_pos;
+out:
+	if (rc && bc_ready)
+		for (k = 0; k < BC_PIPE; k++)
+			cudaStreamSynchronize(BC[k].s);
+	pthread_mutex_unlock(&C.mu);
+	return rc;
+}
+
+int csnappy_bc_decompress_host(const void *h_container, uint64_t container_length, uint32_t page_size, void *h_out,
+			       uint64_t out_capacity, uint64_t *out_length, uint32_t *failed_page)
+{
+	int rc = 0, k, first_err = 0;
+	const uint8_t *cont = (const uint8_t *)h_container;
+	uint32_t nr32 = 0, chunk, max_clen;
+	uint64_t nr, done, ipos, issued = 0, retire_next = 0, produced_total = 0, err_page = 0;
+	const uint32_t *idx;
+	if (page_size == 0 || page_size > CSB_FRAGMENT_MAX)
+		return set_err("page_size outside 1..32768", 0);
+	if (!h_container || !out_length || container_length < 4)
+		return set_err("container missing or shorter than its header", 0);
+	memcpy(&nr32, cont, 4);
+	nr = nr32;
+	if (container_length < 4 + 4 * nr)
+		return CSNAPPY_E_DATA_MALFORMED;
+	if (out_capacity < nr * page_size || (nr && !h_out))
+		return CSNAPPY_E_OUTPUT_INSUF;
+	*out_length = 0;
+	if (nr == 0)
+		return 0;
+	idx = (const uint32_t *)(cont + 4); /* (4-byte aligned if the container is) */
+	ipos = 4 + 4 * nr;
+	chunk = bc_chunk_pages(page_size, nr);
+	max_clen = csnappy_max_compressed_length(page_size);
+
+	pthread_mutex_lock(&C.mu);
+	TRY("stream create", bc_init());
+	for (k = 0; k < BC_PIPE; k++) {
+		struct bc_slot *b = &BC[k];
+		TRY("cudaMalloc(packed)", grow_dev(&b->d_packed, (size_t)chunk * max_clen + 64));
+		TRY("cudaMalloc(clen)", grow_dev(&b->d_clen, (size_t)chunk * 4 + 64));
+		TRY("cudaMalloc(off)", grow_dev(&b->d_off, ((size_t)chunk + 1) * 8 + 64));
+		TRY("cudaMalloc(out)", grow_dev(&b->d_out, (size_t)chunk * page_size + 64));
+		TRY("cudaMalloc(res)", grow_dev(&b->d_res, (size_t)chunk * 8 + 64));
+		TRY("cudaMallocHost(res)", grow_pin(&b->h_res, (size_t)chunk * 8 + 64));
+		b->busy = 0;
+	}
+	for (done = 0; done < nr || retire_next < issued;) {
+		if (retire_next < issued && (issued - retire_next >= BC_PIPE || done >= nr)) {
+			struct bc_slot *b = &BC[retire_next % BC_PIPE];
+			const uint32_t *olen = (const uint32_t *)b->h_res.p;
+			const int32_t *st = (const int32_t *)b->h_res.p + b->n;
+			uint32_t i;
+			TRY("sync", cudaStreamSynchronize(b->s));
+			for (i = 0; i < b->n; i++) {
+				if (st[i] != 0 && (!first_err || b->first + i < err_page)) {
+					first_err = st[i];
+					err_page = b->first + i;
+				}
+				produced_total += olen[i];
+			}
+			retire_next++;
+			continue;
+		}
+		{
+			struct bc_slot *b = &BC[issued % BC_PIPE];
+			uint64_t left_pages = nr - done, bytes = 0;
+			uint32_t nb = left_pages < chunk ? (uint32_t)left_pages : chunk, i, longest = 0;
+			struct csb_decompress_args a;
+			for (i = 0; i < nb; i++) {
+				uint32_t cl;
+				memcpy(&cl, (const uint8_t *)idx + 4 * (done + i), 4);
+				if (cl > max_clen || ipos + bytes + cl > container_length) {
+					/* a size no writer produces, or a payload past the end of the container */
+					if (!first_err) {
+						first_err = CSNAPPY_E_DATA_MALFORMED;
+						err_page = done + i;
+					}
+					nb = i;
+					left_pages = 0;
+					break;
+				}
+				bytes += cl;
+				if (cl > longest)
+					longest = cl;
+			}
+			if (nb) {
+				TRY("H2D payload", cudaMemcpyAsync(b->d_packed.p, cont + ipos, bytes, cudaMemcpyHostToDevice, b->s));
+				TRY("H2D index", cudaMemcpyAsync(b->d_clen.p, (const uint8_t *)idx + 4 * done, (size_t)nb * 4, cudaMemcpyHostToDevice, b->s));
+				TRY("scan launch", csb_launch_scan((const uint32_t *)b->d_clen.p, nb, (uint64_t *)b->d_off.p, (csb_stream_t)b->s));
+				memset(&a, 0, sizeof(a));
+				a.in = (const uint8_t *)b->d_packed.p;
+				a.in_off = (const uint64_t *)b->d_off.p;
+				a.in_len = (const uint32_t *)b->d_clen.p;
+				a.n_blocks = nb;
+				a.out = (uint8_t *)b->d_out.p;
+				a.out_stride = page_size;
+				a.uniform_cap = page_size;
+				a.out_len = (uint32_t *)b->d_res.p;
+				a.status = (int32_t *)b->d_res.p + nb;
+				a.flags = CSNAPPY_BATCH_RAW_IF_FULL;
+				a.max_in_len = longest;
+				a.lanes = g_decompress_lanes;
+				a.ctas_per_sm = g_ctas_per_sm;
+				TRY("decompress launch", csb_launch_decompress(&a, (csb_stream_t)b->s));
+				TRY("D2H pages", cudaMemcpyAsync((uint8_t *)h_out + done * page_size, b->d_out.p, (size_t)nb * page_size,
+								 cudaMemcpyDeviceToHost, b->s));
+				TRY("D2H result", cudaMemcpyAsync(b->h_res.p, b->d_res.p, (size_t)nb * 8, cudaMemcpyDeviceToHost, b->s));
+				b->first = done;
+				b->n = nb;
+				ipos += bytes;
+				done += nb;
+				issued++;
+			}
+			if (left_pages == 0)
+				done = nr; /* stop queueing after a malformed index entry */
+		}
+	}
+	*out_length = produced_total;
+	if (first_err) {
+		if (failed_page)
+			*failed_page = (uint32_t)err_page;
+		rc = first_err;
+	}
+out:
+	if (bc_ready)
+		for (k = 0; k < BC_PIPE; k++)
+			cudaStreamSynchronize(BC[k].s);
+	pthread_mutex_unlock(&C.mu);
+	return rc;
+}

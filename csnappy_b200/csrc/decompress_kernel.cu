@@ -318,8 +318,7 @@ __global__ void __launch_bounds__(kMaxThreadsD) decompress_kernel(const Decompre
 		return;	 // padding lanes of the last warp (no block-wide barriers below)
 	const csb_decompress_args &a = p.a;
 	uint8_t *gs = smem + (size_t)gid * p.group_smem;
-	uint8_t *sin = gs;
-	uint8_t *sout = sin + p.in_area;
+	uint8_t *sout = gs + p.in_area;
 	uint32_t *meta = reinterpret_cast<uint32_t *>(sout + p.out_area);  // G walk words + G descriptors
 	const uint32_t bar = smem_u32(meta + 3 * G);
 	const unsigned full = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
@@ -333,6 +332,8 @@ __global__ void __launch_bounds__(kMaxThreadsD) decompress_kernel(const Decompre
 	int state = DS_NEED;
 	uint32_t parity = 0, blk = 0;
 	StagedState st = {0, 0, 0, 0};
+	uint32_t sin_off = 0;
+	bool raw = false;
 	uint8_t *dst = nullptr;
 
 	for (;;) {
@@ -368,9 +369,15 @@ __global__ void __launch_bounds__(kMaxThreadsD) decompress_kernel(const Decompre
 					ilen -= used;
 				}
 			}
-			if (rc == E_OK && !(ilen + 16 <= p.in_area && cap <= p.out_area)) {
+			if (rc == E_OK && !(ilen + 32 <= p.in_area && cap <= p.out_area)) {
 				uint32_t produced = 0;
-				rc = decode_streaming<G>(g, src, ilen, dst, cap, &produced);
+				if ((a.flags & 4u) && ilen == cap) {  // stored block too large to stage: plain copy
+					for (uint32_t i = g.lane; i < ilen; i += G)
+						dst[i] = src[i];
+					produced = ilen;
+				} else {
+					rc = decode_streaming<G>(g, src, ilen, dst, cap, &produced);
+				}
 				if (g.lane == 0) {
 					a.status[blk] = rc;
 					a.out_len[blk] = rc == E_OK ? produced : 0u;
@@ -392,21 +399,10 @@ __global__ void __launch_bounds__(kMaxThreadsD) decompress_kernel(const Decompre
 			st.produced = 0;
 			st.irem = (int)ilen;
 			st.orem = (int)cap;
-			const bool bulk = (reinterpret_cast<uintptr_t>(src) & 15u) == 0 && ilen >= 16;
-			const uint32_t n16 = bulk ? (ilen & ~15u) : 0;
-			if (bulk) {
-				if (g.lane == 0) {
-					fence_proxy_async();
-					mbar_expect_tx(bar, n16);
-					bulk_g2s(smem_u32(sin), src, n16, bar);
-				}
-				for (uint32_t i = n16 + g.lane; i < ilen; i += G)
-					sin[i] = src[i];
-				state = DS_LOADING;
-			} else {
-				load_block_to_smem<G>(g, sin, src, ilen);
-				state = DS_RUN;
-			}
+			raw = (a.flags & 4u) && ilen == cap;  // stored block (block_compressor.c:378)
+			bool bulk;
+			sin_off = stage_block<G>(g, gs, src, ilen, bar, &bulk);
+			state = bulk ? DS_LOADING : DS_RUN;
 			g.sync();
 		}
 		if (state == DS_LOADING) {
@@ -417,8 +413,22 @@ __global__ void __launch_bounds__(kMaxThreadsD) decompress_kernel(const Decompre
 		}
 
 		int rc = E_OK;
-		if (!decode_batch<G>(g, gs, 0u, p.in_area, lut, meta, st, rc))
+		if (raw) {
+			// stored block: realign the staged bytes into the output area, 16 bytes per lane
+			const uint32_t n = (uint32_t)st.irem;
+			for (uint32_t c = 16 * g.lane; c < n; c += 16 * G) {
+				uint4 v;
+				v.x = lds32u(gs, sin_off + c);
+				v.y = lds32u(gs, sin_off + c + 4);
+				v.z = lds32u(gs, sin_off + c + 8);
+				v.w = lds32u(gs, sin_off + c + 12);
+				*reinterpret_cast<uint4 *>(sout + c) = v;
+			}
+			st.produced = n;
+			g.sync();
+		} else if (!decode_batch<G>(g, gs, sin_off, p.in_area, lut, meta, st, rc)) {
 			continue;
+		}
 
 		// ---- block finished ----
 		const uint32_t produced = st.produced;
@@ -477,7 +487,7 @@ extern "C" int csb_launch_decompress(const struct csb_decompress_args *a, csb_st
 
 	DecompressParams p;
 	p.a = *a;
-	const int G = a->lanes ? a->lanes : 16;
+	const int G = a->lanes ? a->lanes : 32;
 	// staging capacities: output from the (uniform) capacity or the stride, input from the hint,
 	// the stride, or the format's worst case for that output size; both capped at fragment scale
 	uint64_t out_cap = a->out_cap ? a->out_stride : a->uniform_cap;
@@ -491,7 +501,7 @@ extern "C" int csb_launch_decompress(const struct csb_decompress_args *a, csb_st
 	}
 	if (in_cap > 32 + CSB_FRAGMENT_MAX + CSB_FRAGMENT_MAX / 6)
 		in_cap = 32 + CSB_FRAGMENT_MAX + CSB_FRAGMENT_MAX / 6;
-	p.in_area = (uint32_t)((in_cap + 15) & ~15ull) + 16;  // + slack for 4-byte over-reads of a literal source
+	p.in_area = (uint32_t)((in_cap + 15) & ~15ull) + 32;  // + staging shift (< 16) + slack for over-reads
 	p.out_area = (uint32_t)((out_cap + 15) & ~15ull);
 	const uint32_t meta_bytes = 12u * (uint32_t)G + 16u;  // walk words, descriptors, mbarrier
 	p.group_smem = p.in_area + p.out_area + meta_bytes;

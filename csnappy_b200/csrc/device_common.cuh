@@ -77,11 +77,12 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity)
 	return ok != 0;
 }
 
-// little-endian 32-bit load at an arbitrary byte offset of a 4-byte aligned shared-memory area
+// little-endian 32-bit load at an arbitrary byte offset of a shared-memory area (any alignment)
 __device__ __forceinline__ uint32_t lds32u(const uint8_t *area, uint32_t off)
 {
-	const uint32_t *w = reinterpret_cast<const uint32_t *>(area + (off & ~3u));
-	return __funnelshift_r(w[0], w[1], (off & 3u) * 8u);
+	const uintptr_t a = reinterpret_cast<uintptr_t>(area) + off;
+	const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+	return __funnelshift_r(w[0], w[1], ((uint32_t)a & 3u) * 8u);
 }
 
 __device__ __forceinline__ uint4 ldg_stream(const uint4 *p)
@@ -126,6 +127,33 @@ __device__ __forceinline__ void load_block_to_smem(const Group<G> &g, uint8_t *d
 		for (uint32_t i = g.lane; i < n; i += G)
 			dst[i] = src[i];
 	}
+}
+
+// Stage n bytes of global memory at ANY alignment into shared memory: the 16-byte aligned interior
+// travels as one bulk async copy completing on `bar`, the (< 16 byte) head and tail as byte loads.
+// `area` is 16-byte aligned with room for n + 16 bytes; the data lands at area + (src & 15) -- the
+// returned shift -- so that global and shared addresses agree modulo 16.  Reads nothing outside
+// [src, src + n).  *bulk tells whether a bulk copy is in flight (wait for `bar` before reading).
+template <int G>
+__device__ __forceinline__ uint32_t stage_block(const Group<G> &g, uint8_t *area, const uint8_t *src, uint32_t n,
+						uint32_t bar, bool *bulk)
+{
+	const uint32_t s = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15u);
+	uint32_t head = (16u - s) & 15u;
+	if (head > n)
+		head = n;
+	const uint32_t mid = (n - head) & ~15u;
+	*bulk = mid != 0;
+	if (mid && g.lane == 0) {
+		fence_proxy_async();  // earlier generic-proxy accesses to this area precede the async-proxy write
+		mbar_expect_tx(bar, mid);
+		bulk_g2s(smem_u32(area + s + head), src + head, mid, bar);
+	}
+	for (uint32_t i = g.lane; i < head; i += G)
+		area[s + i] = src[i];
+	for (uint32_t i = head + mid + g.lane; i < n; i += G)
+		area[s + i] = src[i];
+	return s;
 }
 
 struct DeviceInfo {

@@ -1,6 +1,6 @@
 /*
  * kernels.h -- C-linkage launchers of the sm_100a kernels, called by the plain-C
- * shim (csnappy_shim.c).  Internal to the library; the public ABI is include/*.h.
+ * shim (csnappy_shim.c).  Internal to the library; the public ABI is in include/.
  */
 #ifndef CSNAPPY_B200_KERNELS_H_
 #define CSNAPPY_B200_KERNELS_H_
@@ -44,7 +44,7 @@ struct csb_decompress_args {
 	uint32_t uniform_cap;
 	uint32_t *out_len;
 	int32_t *status;
-	uint32_t flags;		/* CSNAPPY_BATCH_WITH_HEADER */
+	uint32_t flags;		/* CSNAPPY_BATCH_WITH_HEADER | CSNAPPY_BATCH_RAW_IF_FULL */
 	uint32_t max_in_len;	/* staging hint: longest input block (0 = derive) */
 	int lanes;
 	int ctas_per_sm;
@@ -55,6 +55,10 @@ int csb_launch_compress(const struct csb_compress_args *a, csb_stream_t s);
 int csb_launch_decompress(const struct csb_decompress_args *a, csb_stream_t s);
 int csb_launch_pack(const uint8_t *slots, uint64_t slot_stride, const uint32_t *len,
 		    uint32_t n_blocks, uint8_t *packed, uint64_t *off, csb_stream_t s);
+int csb_launch_pack_stored(const uint8_t *slots, uint64_t slot_stride, const uint32_t *len, uint32_t n_blocks,
+			   const uint8_t *in, uint32_t page_len, uint64_t total_in, uint32_t *clen,
+			   uint8_t *packed, uint64_t *off, csb_stream_t s);
+int csb_launch_scan(const uint32_t *len, uint32_t n_blocks, uint64_t *off, csb_stream_t s);
 uint64_t csb_launch_count(void);
 
 #ifdef __cplusplus

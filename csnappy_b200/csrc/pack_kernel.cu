@@ -43,6 +43,24 @@ int device_info(DeviceInfo *out)
 
 constexpr int kScanThreads = 1024;
 
+// Stored-block rule of block_compressor.c:316-318: a block whose compressed size is not smaller than
+// its input is kept raw, and its recorded size is the input size.  page_len == 0 disables the rule.
+__device__ __forceinline__ uint32_t block_in_len(uint32_t i, uint32_t page_len, uint64_t total_in)
+{
+	const uint64_t at = (uint64_t)i * page_len;
+	const uint64_t left = total_in > at ? total_in - at : 0;
+	return left < page_len ? (uint32_t)left : page_len;
+}
+
+__global__ void __launch_bounds__(256) clamp_kernel(const uint32_t *__restrict__ len, uint32_t n, uint32_t page_len,
+						    uint64_t total_in, uint32_t *__restrict__ clen)
+{
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const uint32_t ilen = block_in_len(i, page_len, total_in);
+		clen[i] = len[i] >= ilen ? ilen : len[i];
+	}
+}
+
 // single-CTA exclusive scan: off[i] = sum(len[0..i)), off[n] = total
 __global__ void __launch_bounds__(kScanThreads) scan_kernel(const uint32_t *__restrict__ len, uint32_t n,
 							    uint64_t *__restrict__ off)
@@ -74,16 +92,22 @@ __global__ void __launch_bounds__(kScanThreads) scan_kernel(const uint32_t *__re
 
 // one warp per block: packed[off[i] .. off[i]+len[i]) = slots[i*stride ..).  Destination words are
 // written 4-byte aligned; the (arbitrarily aligned) source is realigned with a funnel shift.
+// With `raw` set, block i comes from raw + i * page_len instead of its slot when its compressed
+// size (slot_len[i]) is not smaller than its input (the stored-block rule above).
 __global__ void __launch_bounds__(256) gather_kernel(const uint8_t *__restrict__ slots, uint64_t stride,
 						     const uint32_t *__restrict__ len, uint32_t n,
-						     uint8_t *__restrict__ packed, const uint64_t *__restrict__ off)
+						     uint8_t *__restrict__ packed, const uint64_t *__restrict__ off,
+						     const uint8_t *__restrict__ raw, uint32_t page_len,
+						     uint64_t total_in, const uint32_t *__restrict__ slot_len)
 {
 	const uint32_t lane = threadIdx.x & 31u;
 	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
 	for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
-		const uint8_t *src = slots + (uint64_t)i * stride;
-		uint8_t *dst = packed + off[i];
 		const uint32_t m = len[i];
+		const uint8_t *src = slots + (uint64_t)i * stride;
+		if (raw && slot_len[i] >= block_in_len(i, page_len, total_in))
+			src = raw + (uint64_t)i * page_len;
+		uint8_t *dst = packed + off[i];
 		uint32_t head = (uint32_t)((4u - (reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u);
 		if (head > m)
 			head = m;
@@ -129,9 +153,50 @@ extern "C" int csb_launch_pack(const uint8_t *slots, uint64_t slot_stride, const
 		long ctas = ((long)n_blocks + 7) / 8;
 		if (ctas > (long)di.sm_count * 8)
 			ctas = (long)di.sm_count * 8;
-		gather_kernel<<<(int)ctas, 256, 0, s>>>(slots, slot_stride, len, n_blocks, packed, off);
+		gather_kernel<<<(int)ctas, 256, 0, s>>>(slots, slot_stride, len, n_blocks, packed, off, nullptr, 0, 0, nullptr);
 		count_launch();
 		e = (int)cudaGetLastError();
 	}
 	return e;
+}
+
+// Pack with the stored-block rule: clen[i] = min(len[i], input length of block i); off = exclusive
+// scan of clen; packed gets the slot bytes, or the raw input block where compression did not help.
+extern "C" int csb_launch_pack_stored(const uint8_t *slots, uint64_t slot_stride, const uint32_t *len, uint32_t n_blocks,
+				      const uint8_t *in, uint32_t page_len, uint64_t total_in, uint32_t *clen,
+				      uint8_t *packed, uint64_t *off, csb_stream_t s)
+{
+	DeviceInfo di;
+	int e = device_info(&di);
+	if (e)
+		return e;
+	if (n_blocks == 0) {
+		scan_kernel<<<1, kScanThreads, 0, s>>>(len, 0, off);
+		count_launch();
+		return (int)cudaGetLastError();
+	}
+	long ctas = ((long)n_blocks + 255) / 256;
+	if (ctas > (long)di.sm_count * 4)
+		ctas = (long)di.sm_count * 4;
+	clamp_kernel<<<(int)ctas, 256, 0, s>>>(len, n_blocks, page_len, total_in, clen);
+	count_launch();
+	if ((e = (int)cudaGetLastError()))
+		return e;
+	scan_kernel<<<1, kScanThreads, 0, s>>>(clen, n_blocks, off);
+	count_launch();
+	if ((e = (int)cudaGetLastError()))
+		return e;
+	ctas = ((long)n_blocks + 7) / 8;
+	if (ctas > (long)di.sm_count * 8)
+		ctas = (long)di.sm_count * 8;
+	gather_kernel<<<(int)ctas, 256, 0, s>>>(slots, slot_stride, clen, n_blocks, packed, off, in, page_len, total_in, len);
+	count_launch();
+	return (int)cudaGetLastError();
+}
+
+extern "C" int csb_launch_scan(const uint32_t *len, uint32_t n_blocks, uint64_t *off, csb_stream_t s)
+{
+	scan_kernel<<<1, kScanThreads, 0, s>>>(len, n_blocks, off);
+	count_launch();
+	return (int)cudaGetLastError();
 }

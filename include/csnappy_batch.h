@@ -42,6 +42,9 @@ extern "C" {
 #define CSNAPPY_BATCH_WITH_HEADER 0x2u  /* decompress: blocks start with a varint32 length;
 					   csnappy_decompress() semantics incl. -1 / -2
 					   (csnappy_decompress.c:394-411) */
+#define CSNAPPY_BATCH_RAW_IF_FULL 0x4u  /* decompress: a block whose input length equals its
+					   output capacity is a stored block and is copied
+					   (block_compressor.c:378) */
 
 /*
  * Batched csnappy_compress_fragment (csnappy_compress.c:469-606).
@@ -100,6 +103,30 @@ int csnappy_batch_decompress_host(const void *h_in, uint64_t in_stride,
 				  void *h_out, uint64_t out_stride,
 				  uint32_t uniform_out_cap, uint32_t *h_out_len,
 				  int32_t *h_status, uint32_t flags);
+
+/*
+ * block_compressor-style page container on HOST buffers (reference block_compressor.c:275-394):
+ *     [u32 nr_pages][u32 clen[nr_pages]][payload_0]...[payload_{nr_pages-1}]
+ * payload_i = csnappy_compress_fragment(page_i, wm), or the page itself when that is not smaller
+ * (clen_i = page length, :316-318); a reader takes clen_i == page_size as "stored" (:378) -- the
+ * reference's wart that a stored PARTIAL last page is not recognised is reproduced, not fixed.
+ * The bytes written are identical to what block_compressor's writer loop produces with csnappy
+ * and WMSIZE_ORDER = workmem_bytes_power_of_two (:99).  Chunks of pages are pipelined through the
+ * device (H2D / kernels / D2H overlap); only compressed bytes cross the bus on the compressed side.
+ *
+ * csnappy_bc_compress_host    container_capacity >= csnappy_bc_max_container_length(); returns 0,
+ *                             CSNAPPY_E_DEVICE or CSNAPPY_E_BAD_ARG.
+ * csnappy_bc_decompress_host  out_capacity >= nr_pages * page_size (CSNAPPY_E_OUTPUT_INSUF else);
+ *                             returns 0 or the code of the first failing page (its index goes to
+ *                             *failed_page when given); *out_length = bytes produced.
+ */
+uint64_t csnappy_bc_max_container_length(uint64_t input_length, uint32_t page_size);
+int csnappy_bc_compress_host(const void *h_in, uint64_t input_length, uint32_t page_size,
+			     void *h_container, uint64_t container_capacity,
+			     uint64_t *container_length, int workmem_bytes_power_of_two);
+int csnappy_bc_decompress_host(const void *h_container, uint64_t container_length,
+			       uint32_t page_size, void *h_out, uint64_t out_capacity,
+			       uint64_t *out_length, uint32_t *failed_page);
 
 /*
  * Library / device introspection and kernel tuning knobs (used by bench.py and

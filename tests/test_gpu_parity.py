@@ -272,6 +272,95 @@ def test_batch_pack(cs):
         assert (p[off[i]: off[i] + lens[i]] == slots[i, : lens[i]]).all(), i
 
 
+# --------------------------------------------------------------------------- block_compressor container
+def _ref_container(chk, data: bytes, page: int, wm: int) -> bytes:
+    """block_compressor.c:275-345 restated with the oracle as the page compressor."""
+    nr = (len(data) + page - 1) // page
+    idx, payload = [], []
+    for i in range(nr):
+        p = data[i * page:(i + 1) * page]
+        c = chk.compress_fragment(p, wm)
+        if len(c) >= len(p):
+            c = p
+        idx.append(len(c))
+        payload.append(c)
+    return struct.pack("<I", nr) + b"".join(struct.pack("<I", x) for x in idx) + b"".join(payload)
+
+
+@pytest.mark.parametrize("page,wm", [(4096, 13), (1024, 11), (32768, 15)])
+def test_bc_container_matches_reference_writer_and_round_trips(cs, chk, urls, page, wm):
+    rng = np.random.default_rng(21)
+    data = (urls[:150000] + rng.integers(0, 256, 3 * page + 17, dtype=np.uint8).tobytes() + bytes(5 * page) +
+            urls[150000:150000 + 2 * page + 1234])
+    h_in = np.frombuffer(data, dtype=np.uint8).copy()
+    cont = np.zeros(cs.api.bc_max_container_length(len(data), page), dtype=np.uint8)
+    clen = cs.api.bc_compress_host(h_in, len(data), cont, wm, page)
+    ref = _ref_container(chk, data, page, wm)
+    assert clen == len(ref) and cont[:clen].tobytes() == ref
+    nr = (len(data) + page - 1) // page
+    out = np.zeros(nr * page, dtype=np.uint8)
+    rc, olen, bad = cs.api.bc_decompress_host(cont, clen, out, page)
+    assert (rc, olen, bad) == (0, len(data), None) and out[:olen].tobytes() == data
+
+
+def test_bc_container_many_chunks_and_errors(cs, chk):
+    """More pages than one pipeline chunk (8192 x 4 KiB), then corrupt / truncated containers."""
+    from csnappy_b200 import synth
+
+    B, page = 20000, 4096
+    h_in = synth.mixed_pages(B, page, seed=77, device="cuda", pool_bytes=1 << 20).cpu().numpy()
+    cont = np.zeros(cs.api.bc_max_container_length(B * page, page), dtype=np.uint8)
+    clen = cs.api.bc_compress_host(h_in, B * page, cont, 13, page)
+    idx = cont[4:4 + 4 * B].view(np.uint32)
+    ref_out, ref_len, _ = oracle.batch_compress(h_in.reshape(B, page), 13, chk.kind, threads=4)
+    want = np.minimum(ref_len, page)
+    assert int(cont[:4].view(np.uint32)[0]) == B and (idx == want).all() and clen == 4 + 4 * B + int(want.sum())
+    off = 4 + 4 * B + np.concatenate([[0], np.cumsum(want.astype(np.int64))])
+    for i in list(range(0, B, 997)) + [B - 1]:
+        exp = h_in[i * page:(i + 1) * page] if ref_len[i] >= page else ref_out[i, : ref_len[i]]
+        assert (cont[off[i]: off[i + 1]] == exp).all(), i
+    out = np.zeros(B * page, dtype=np.uint8)
+    rc, olen, bad = cs.api.bc_decompress_host(cont, clen, out, page)
+    assert (rc, olen, bad) == (0, B * page, None) and (out == h_in).all()
+    # corrupt one compressed page (first text page after page 9000): its decode must fail or differ, never crash
+    victim = next(i for i in range(9000, B) if 100 < idx[i] < page)
+    broken = cont[:clen].copy()
+    broken[off[victim] + 1: off[victim] + 40] = 0xFF
+    rc, _, bad = cs.api.bc_decompress_host(broken, clen, out, page)
+    exp_rc = chk.decompress_noheader(broken[off[victim]: off[victim + 1]].tobytes(), page)[0]
+    assert exp_rc != 0 and (rc, bad) == (exp_rc, victim)
+    # truncated payload and truncated index
+    assert cs.api.bc_decompress_host(cont[: clen - 5].copy(), clen - 5, out, page)[0] == cs.CSNAPPY_E_DATA_MALFORMED
+    assert cs.api.bc_decompress_host(cont[:1000].copy(), 1000, out, page)[0] == cs.CSNAPPY_E_DATA_MALFORMED
+    assert cs.api.bc_decompress_host(cont, clen, out[: page * 10], page)[0] == cs.CSNAPPY_E_OUTPUT_INSUF
+
+
+def test_batch_decompress_raw_if_full_flag(cs, chk):
+    rng = np.random.default_rng(31)
+    page = 4096
+    raw = rng.integers(0, 256, page, dtype=np.uint8).tobytes()
+    text = bytes(rng.integers(97, 100, page, dtype=np.uint8))
+    streams = [raw, chk.compress_fragment(text, 13), raw[::-1], chk.compress_fragment(raw, 13)]
+    expect = [raw, text, raw[::-1], raw]
+    off = np.cumsum([0] + [len(s) for s in streams])  # packed back to back: arbitrary alignment
+    host = np.frombuffer(b"".join(streams), dtype=np.uint8).copy()
+    d_in = torch.from_numpy(host).cuda()
+    d_off = torch.from_numpy(off[:-1].astype(np.int64)).cuda()
+    d_len = torch.tensor([len(s) for s in streams], dtype=torch.int32).cuda()
+    for lanes in (8, 16, 32):
+        cs.set_tuning("decompress_lanes", lanes)
+        try:
+            out, out_len, status = cs.batch_decompress(d_in, d_len, len(streams), page, in_off=d_off, out_stride=page,
+                                                       flags=cs.api.BATCH_RAW_IF_FULL)
+            torch.cuda.synchronize()
+        finally:
+            cs.set_tuning("decompress_lanes", 0)
+        o = out.cpu().numpy()
+        assert status.cpu().tolist() == [0, 0, 0, 0] and out_len.cpu().tolist() == [page] * 4
+        for i, e in enumerate(expect):
+            assert o[i * page:(i + 1) * page].tobytes() == e, (i, lanes)
+
+
 # --------------------------------------------------------------------------- host batches + scale properties
 def test_host_batch_roundtrip(cs, chk):
     pages = fuzz_pages(2024, 3000, 4096)
