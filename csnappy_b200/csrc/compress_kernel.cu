@@ -136,7 +136,7 @@ __device__ __forceinline__ uint32_t emit_copy(const Group<G> &g, uint8_t *dst, u
 enum : int { ST_NEED = 0, ST_LOADING = 1, ST_RUN = 2 };
 
 template <int G>
-__global__ void __launch_bounds__(kMaxThreads) compress_kernel(const CompressParams p)
+__global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const CompressParams p)
 {
 	extern __shared__ __align__(128) uint8_t smem[];
 	const Group<G> g;

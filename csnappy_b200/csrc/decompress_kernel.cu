@@ -121,37 +121,38 @@ __device__ __forceinline__ int decode_streaming(const Group<G> &g, const uint8_t
 }
 
 // ---- staged path: one batch of up to G tags ---------------------------------------------------
-struct StagedState {
-	uint32_t pos, produced;	 // input / output cursor
-	int irem, orem;		 // input bytes left, output capacity left
-};
-
 // Returns 1 when the stream is finished (rc says how), 0 to continue with the next batch.
-// gs = the group's shared memory; sin_off / sout_off = offsets of the staged input / output in it.
+// gs = the group's shared memory; sin_off / sout_off = offsets of the staged input / output in it;
+// lut_a / meta_a = shared addresses of the walk table and of the group's G walk words + G descriptors.
 template <int G>
 __device__ __forceinline__ int decode_batch(const Group<G> &g, uint8_t *gs, uint32_t sin_off, uint32_t sout_off,
-					    const uint32_t *lut, uint32_t *meta, StagedState &st, int &rc)
+					    uint32_t lut_a, uint32_t meta_a, uint32_t &st_pos, uint32_t &st_produced,
+					    int &st_irem, int &st_orem, int &rc)
 {
 	const uint8_t *sin = gs + sin_off;
-	uint32_t pos = st.pos, produced = st.produced;
-	int irem = st.irem, orem = st.orem;
+	const uint32_t gs_a = smem_u32(gs), sin_a = gs_a + sin_off, sout_a = gs_a + sout_off;
+	int irem = st_irem, orem = st_orem;
 	// ---- walk: positions and output offsets of up to G tags; ONE exit test per tag ----
 	// lut[tag] = input bytes of the whole tag | output bytes << 16; a long literal has 0xffff input
 	// bytes, so "input exhausted", "long literal", "payload cut off" and "no space" all show up as a
-	// negative remainder and are told apart once, after the loop.
+	// negative remainder and are told apart once, after the loop.  pos | produced << 16 advances with
+	// one packed add.
+	uint32_t state = st_pos | (st_produced << 16), ra = sin_a + st_pos;
 	uint32_t k = 0, e = 0;
-#pragma unroll 4
+#pragma unroll 8
 	for (; k < (uint32_t)G; ++k) {
-		e = lut[sin[pos]];
-		meta[k] = pos | (produced << 16);
-		const int x = irem - (int)(e & 0xffffu), y = orem - (int)(e >> 16);
+		e = lds_u32(lut_a + 4 * lds_u8(ra));
+		sts_u32(meta_a + 4 * k, state);
+		const uint32_t adv = e & 0xffffu;
+		const int x = irem - (int)adv, y = orem - (int)(e >> 16);
 		if ((x | y) < 0)
 			break;
-		pos += e & 0xffffu;
-		produced += e >> 16;
+		state += e;
+		ra += adv;
 		irem = x;
 		orem = y;
 	}
+	uint32_t pos = state & 0xffffu, produced = state >> 16;
 	const uint32_t ntags = k;  // complete tags of this batch
 	int werr = E_OK;
 	bool stop = false, longlit = false;
@@ -168,26 +169,27 @@ __device__ __forceinline__ int decode_batch(const Group<G> &g, uint8_t *gs, uint
 	g.sync();
 
 	// ---- decode: lane k owns tag k (plus the tag that ran out of space: offset check only) ----
+	// descriptor: x = source shared address | len << 20 | overlap << 28, y = destination shared address | period << 20
 	uint32_t d0 = 0, d1 = 0;
 	bool bad = false;
 	if (g.lane < ntags + (werr == E_OUTPUT_OVERRUN ? 1u : 0u)) {
-		const uint32_t mp = meta[g.lane];
-		const uint32_t p = mp & 0xffffu, o = mp >> 16;
-		const uint32_t tag = sin[p];
+		const uint32_t mp = lds_u32(meta_a + 4 * g.lane);
+		const uint32_t p = sin_a + (mp & 0xffffu), o = mp >> 16;
+		const uint32_t tag = lds_u8(p);
 		const uint32_t kind = tag & 3u;
 		uint32_t len = (tag >> 2) + 1;
-		d1 = sout_off + o;
+		d1 = sout_a + o;
 		if (kind == 0) {
-			d0 = (sin_off + p + 1) | (len << 20);  // literal: source is the input
+			d0 = (p + 1) | (len << 20);  // literal: source is the input
 		} else {
-			uint32_t off = sin[p + 1];
+			uint32_t off = lds_u8(p + 1);
 			if (kind == 1) {
 				len = ((tag >> 2) & 7u) + 4;
 				off |= (tag >> 5) << 8;
 			} else {
-				off |= (uint32_t)sin[p + 2] << 8;
+				off |= lds_u8(p + 2) << 8;
 				if (kind == 3)
-					off |= ((uint32_t)sin[p + 3] << 16) | ((uint32_t)sin[p + 4] << 24);
+					off |= (lds_u8(p + 3) << 16) | (lds_u8(p + 4) << 24);
 			}
 			bad = off - 1u >= o;  // off == 0 or off > produced, csnappy_decompress.c:302
 			d0 = ((d1 - off) & 0xfffffu) | (len << 20);
@@ -203,38 +205,36 @@ __device__ __forceinline__ int decode_batch(const Group<G> &g, uint8_t *gs, uint
 		rc = badmask ? E_DATA_MALFORMED : werr;
 		return 1;
 	}
-	uint2 *desc = reinterpret_cast<uint2 *>(meta + G);
-	desc[g.lane] = make_uint2(d0, d1);
+	const uint32_t desc_a = meta_a + 4 * G;
+	sts_v2(desc_a + 8 * g.lane, d0, d1);
 	g.sync();
 
 	// ---- execute in stream order, all lanes moving bytes ----
 	for (uint32_t t = 0; t < ntags; ++t) {
-		const uint2 d = desc[t];
-		const uint8_t *from = gs + (d.x & 0xfffffu);
-		uint8_t *to = gs + (d.y & 0xfffffu);
+		const uint2 d = lds_v2(desc_a + 8 * t);
+		const uint32_t from = (d.x & 0xfffffu) + g.lane, to = (d.y & 0xfffffu) + g.lane;
 		const uint32_t len = (d.x >> 20) & 0xffu;
-		if (!(d.x >> 28)) {
+		if (d.x < (1u << 28)) {
 			// literal or disjoint copy (len <= 64)
 			for (uint32_t i = g.lane; i < len; i += G)
-				to[i] = from[i];
+				sts_u8(to + i - g.lane, lds_u8(from + i - g.lane));
 		} else {
 			const uint32_t off = d.y >> 20;
 			if (off == 1) {
-				const uint8_t v = from[0];
+				const uint32_t v = lds_u8(from - g.lane);
 				for (uint32_t i = g.lane; i < len; i += G)
-					to[i] = v;
+					sts_u8(to + i - g.lane, v);
 			} else if (off >= (uint32_t)G) {
 				// a round of G bytes only reads what earlier rounds wrote
 				for (uint32_t c = 0; c < len; c += G) {
-					const uint32_t i = c + g.lane;
-					if (i < len)
-						to[i] = from[i];
+					if (c + g.lane < len)
+						sts_u8(to + c, lds_u8(from + c));
 					g.sync();
 				}
 			} else {
 				// short period: byte i repeats the pattern [o - off, o)
 				for (uint32_t i = g.lane; i < len; i += G)
-					to[i] = from[i % off];
+					sts_u8(to + i - g.lane, lds_u8(from - g.lane + i % off));
 			}
 		}
 		g.sync();
@@ -280,10 +280,10 @@ __device__ __forceinline__ int decode_batch(const Group<G> &g, uint8_t *gs, uint
 		orem -= (int)len;
 		g.sync();
 	}
-	st.pos = pos;
-	st.produced = produced;
-	st.irem = irem;
-	st.orem = orem;
+	st_pos = pos;
+	st_produced = produced;
+	st_irem = irem;
+	st_orem = orem;
 	if (stop) {
 		rc = E_OK;
 		return 1;
@@ -294,7 +294,7 @@ __device__ __forceinline__ int decode_batch(const Group<G> &g, uint8_t *gs, uint
 enum : int { DS_NEED = 0, DS_LOADING = 1, DS_RUN = 2 };
 
 template <int G>
-__global__ void __launch_bounds__(kMaxThreadsD) decompress_kernel(const DecompressParams p)
+__global__ void __launch_bounds__(kMaxThreadsD, 1) decompress_kernel(const DecompressParams p)
 {
 	extern __shared__ __align__(128) uint8_t smem[];
 	__shared__ uint32_t lut[256];
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(kMaxThreadsD) decompress_kernel(const Decompre
 	uint8_t *gs = smem + (size_t)gid * p.group_smem;
 	uint8_t *sout = gs + p.in_area;
 	uint32_t *meta = reinterpret_cast<uint32_t *>(sout + p.out_area);  // G walk words + G descriptors
-	const uint32_t bar = smem_u32(meta + 3 * G);
+	const uint32_t bar = smem_u32(meta + 3 * G), meta_a = smem_u32(meta), lut_a = smem_u32(lut);
 	const unsigned full = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
 
 	if (g.lane == 0) {
@@ -331,7 +331,8 @@ __global__ void __launch_bounds__(kMaxThreadsD) decompress_kernel(const Decompre
 
 	int state = DS_NEED;
 	uint32_t parity = 0, blk = 0;
-	StagedState st = {0, 0, 0, 0};
+	uint32_t st_pos = 0, st_produced = 0;  // input / output cursor of the staged block
+	int st_irem = 0, st_orem = 0;	       // input bytes left, output capacity left
 	uint32_t sin_off = 0;
 	bool raw = false;
 	uint8_t *dst = nullptr;
@@ -395,10 +396,10 @@ __global__ void __launch_bounds__(kMaxThreadsD) decompress_kernel(const Decompre
 			if (g.lane == 0)
 				bulk_wait_read0();
 			g.sync();
-			st.pos = 0;
-			st.produced = 0;
-			st.irem = (int)ilen;
-			st.orem = (int)cap;
+			st_pos = 0;
+			st_produced = 0;
+			st_irem = (int)ilen;
+			st_orem = (int)cap;
 			raw = (a.flags & 4u) && ilen == cap;  // stored block (block_compressor.c:378)
 			bool bulk;
 			sin_off = stage_block<G>(g, gs, src, ilen, bar, &bulk);
@@ -415,7 +416,7 @@ __global__ void __launch_bounds__(kMaxThreadsD) decompress_kernel(const Decompre
 		int rc = E_OK;
 		if (raw) {
 			// stored block: realign the staged bytes into the output area, 16 bytes per lane
-			const uint32_t n = (uint32_t)st.irem;
+			const uint32_t n = (uint32_t)st_irem;
 			for (uint32_t c = 16 * g.lane; c < n; c += 16 * G) {
 				uint4 v;
 				v.x = lds32u(gs, sin_off + c);
@@ -424,14 +425,14 @@ __global__ void __launch_bounds__(kMaxThreadsD) decompress_kernel(const Decompre
 				v.w = lds32u(gs, sin_off + c + 12);
 				*reinterpret_cast<uint4 *>(sout + c) = v;
 			}
-			st.produced = n;
+			st_produced = n;
 			g.sync();
-		} else if (!decode_batch<G>(g, gs, sin_off, p.in_area, lut, meta, st, rc)) {
+		} else if (!decode_batch<G>(g, gs, sin_off, p.in_area, lut_a, meta_a, st_pos, st_produced, st_irem, st_orem, rc)) {
 			continue;
 		}
 
 		// ---- block finished ----
-		const uint32_t produced = st.produced;
+		const uint32_t produced = st_produced;
 		if (rc == E_OK) {
 			if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
 				const uint32_t n16 = produced & ~15u;

@@ -129,6 +129,38 @@ __device__ __forceinline__ void load_block_to_smem(const Group<G> &g, uint8_t *d
 	}
 }
 
+// explicit shared-space accesses on 32-bit shared addresses (no generic-pointer arithmetic in hot loops)
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a)
+{
+	uint32_t v;
+	asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+	return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a)
+{
+	uint32_t v;
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+	return v;
+}
+__device__ __forceinline__ uint2 lds_v2(uint32_t a)
+{
+	uint2 v;
+	asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+	return v;
+}
+__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v)
+{
+	asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v)
+{
+	asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts_v2(uint32_t a, uint32_t x, uint32_t y)
+{
+	asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+
 // Stage n bytes of global memory at ANY alignment into shared memory: the 16-byte aligned interior
 // travels as one bulk async copy completing on `bar`, the (< 16 byte) head and tail as byte loads.
 // `area` is 16-byte aligned with room for n + 16 bytes; the data lands at area + (src & 15) -- the
