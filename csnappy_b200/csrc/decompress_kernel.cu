@@ -215,9 +215,11 @@ __device__ __forceinline__ int decode_batch(const Group<G> &g, uint8_t *gs, uint
 		const uint32_t from = (d.x & 0xfffffu) + g.lane, to = (d.y & 0xfffffu) + g.lane;
 		const uint32_t len = (d.x >> 20) & 0xffu;
 		if (d.x < (1u << 28)) {
-			// literal or disjoint copy (len <= 64)
-			for (uint32_t i = g.lane; i < len; i += G)
-				sts_u8(to + i - g.lane, lds_u8(from + i - g.lane));
+			// literal or disjoint copy (len <= 64): at most 64 / G predicated rounds, no loop
+#pragma unroll
+			for (uint32_t j = 0; j < 64u / G; ++j)
+				if (g.lane + j * G < len)
+					sts_u8(to + j * G, lds_u8(from + j * G));
 		} else {
 			const uint32_t off = d.y >> 20;
 			if (off == 1) {
