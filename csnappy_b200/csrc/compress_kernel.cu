@@ -48,9 +48,10 @@ struct CompressParams {
 
 // literal tag + payload, csnappy_compress.c:332-371.  Returns bytes written.
 template <int G>
-__device__ __forceinline__ uint32_t emit_literal(const Group<G> &g, uint8_t *dst, const uint8_t *sin, uint32_t src,
+__device__ __forceinline__ uint32_t emit_literal(const Group<G> &g, uint8_t *dst, uint32_t sin_a, uint32_t src,
 						 uint32_t len)
 {
+	src += sin_a;  // shared byte address of the payload
 	const uint32_t v = len - 1;
 	uint32_t hb, hdr;
 	if (v < 60) {
@@ -67,7 +68,7 @@ __device__ __forceinline__ uint32_t emit_literal(const Group<G> &g, uint8_t *dst
 	if (total <= (uint32_t)G) {
 		// common case: header and payload in one store
 		if (g.lane < total)
-			dst[g.lane] = g.lane < hb ? (uint8_t)(hdr >> (8 * g.lane)) : sin[src + g.lane - hb];
+			dst[g.lane] = g.lane < hb ? (uint8_t)(hdr >> (8 * g.lane)) : (uint8_t)lds_u8(src + g.lane - hb);
 		return total;
 	}
 	if (g.lane < hb)
@@ -75,19 +76,19 @@ __device__ __forceinline__ uint32_t emit_literal(const Group<G> &g, uint8_t *dst
 	dst += hb;
 	if (len <= 4u * G) {
 		for (uint32_t i = g.lane; i < len; i += G)
-			dst[i] = sin[src + i];
+			dst[i] = (uint8_t)lds_u8(src + i);
 	} else {
 		// word stores: head bytes up to a 4-byte aligned destination, realigned source words, tail
 		const uint32_t head = (uint32_t)(-(intptr_t)dst) & 3u;
 		if (g.lane < head)
-			dst[g.lane] = sin[src + g.lane];
+			dst[g.lane] = (uint8_t)lds_u8(src + g.lane);
 		const uint32_t words = (len - head) >> 2;
 		uint32_t *dw = reinterpret_cast<uint32_t *>(dst + head);
 		for (uint32_t w = g.lane; w < words; w += G)
-			dw[w] = lds32u(sin, src + head + 4 * w);
+			dw[w] = lds32u_a(src + head + 4 * w);
 		const uint32_t tail = head + (words << 2);
 		if (tail + g.lane < len)
-			dst[tail + g.lane] = sin[src + tail + g.lane];
+			dst[tail + g.lane] = (uint8_t)lds_u8(src + tail + g.lane);
 	}
 	return total;
 }
@@ -147,7 +148,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 	uint8_t *gs = smem + (size_t)gid * p.group_smem;
 	uint16_t *tab = reinterpret_cast<uint16_t *>(gs);
 	uint8_t *sarea = gs + p.table_bytes;  // staged input, 16-byte aligned
-	const uint8_t *sin = sarea;	      // + (src & 15): where the block's first byte lands
+	const uint32_t sarea_a = smem_u32(sarea), tab_a = smem_u32(tab);
+	uint32_t sin_a = sarea_a;  // + (src & 15): shared address where the block's first byte lands
 	const uint32_t bar = smem_u32(sarea + p.in_area);
 	const unsigned full = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
 
@@ -206,7 +208,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 					t4[i] = z;
 			}
 			bool bulk;
-			sin = sarea + stage_block<G>(g, sarea, src, n, bar, &bulk);
+			sin_a = sarea_a + stage_block<G>(g, sarea, src, n, bar, &bulk);
 			state = bulk ? ST_LOADING : ST_RUN;
 			g.sync();
 		}
@@ -239,41 +241,39 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 			s = (32u + j0 + g.lane) >> 5;
 		}
 		const bool valid = pp + s <= ip_limit;
-		const uint32_t bytes = lds32u(sin, valid ? pp : 0u);
-		const uint32_t h = (bytes * kHashMul) >> shift;
-		const uint32_t old = tab[h];
+		const uint32_t bytes = lds32u_a(sin_a + (valid ? pp : 0u));
+		const uint32_t slot = tab_a + 2 * ((bytes * kHashMul) >> shift);
+		const uint32_t old = lds_u16(slot);
 		g.sync();
 		if (valid)
-			tab[h] = (uint16_t)pp;
+			sts_u16(slot, pp);
 		g.sync();
-		const bool exact = g.ballot(valid && tab[h] != pp) != 0;  // two lanes share a slot
+		const bool exact = g.ballot(valid && lds_u16(slot) != pp) != 0;  // two lanes share a slot
 		// candidate: the table -- or, with shared slots, the latest lower lane with the same hash
 		// (invalid lanes must not follow a stale entry: blocks under 15 bytes never clear the table)
 		uint32_t cand = valid ? old : 0u;
 		unsigned same = 0;
 		if (exact) {
 			if (valid)
-				tab[h] = (uint16_t)old;	 // back to the state before this window
-			same = g.match(valid ? h : (0x80000000u | g.lane));
+				sts_u16(slot, old);  // back to the state before this window
+			same = g.match(valid ? slot : (0x80000000u | g.lane));
 			const unsigned lower = same & ((1u << g.lane) - 1u);
 			const uint32_t lp = g.bcast(pp, lower ? 31 - __clz(lower) : (int)g.lane);
 			if (lower)
 				cand = lp;
 			g.sync();
 		}
-		const uint32_t cb = lds32u(sin, cand);
+		const uint32_t cb = lds32u_a(sin_a + cand);
 		const unsigned H = g.ballot(valid && cb == bytes);
 		const unsigned V = g.ballot(valid);
 		const bool multi = uni && !exact;
 
-		unsigned I = 0;	   // lanes whose insert stands
-		uint32_t ins = 0;  // first inserting lane of the current run
-		uint32_t cur = t;  // first lane that may hit
+		uint32_t cur = t;      // first lane that may hit
+		unsigned fhit = 32;    // exact windows: the (single) hit lane
 		bool fin = false;
 		for (;;) {
 			const unsigned elig = H & (full << cur) & full;
 			if (!elig) {
-				I |= full << ins;
 				if (V != full) {
 					fin = true;  // ran into ip_limit without a hit
 				} else if (uni) {
@@ -290,20 +290,20 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 				break;
 			}
 			const unsigned f = __ffs(elig) - 1;
-			I |= (full << ins) & ((2u << f) - 1u);
 			const uint32_t ip = g.bcast(pp, (int)f), cd = g.bcast(cand, (int)f);
 			// match extension, bounded by n (csnappy_compress.c:252-295): the first G bytes one
 			// byte per lane (most copies end there), then 4*G bytes per step
 			const uint32_t room = n - ip;
+			const uint32_t ip_a = sin_a + ip, cd_a = sin_a + cd;
 			uint32_t m;
 			{
-				const unsigned ne = g.ballot(sin[cd + 4 + g.lane] != sin[ip + 4 + g.lane] || 4 + g.lane >= room);
+				const unsigned ne = g.ballot(lds_u8(cd_a + 4 + g.lane) != lds_u8(ip_a + 4 + g.lane) || 4 + g.lane >= room);
 				m = 3 + __ffs(ne);
 				if (!ne) {
 					m = 4 + G;
 					for (;;) {
 						const uint32_t d = min(m + 4 * g.lane, room);
-						const uint32_t x = lds32u(sin, cd + d) ^ lds32u(sin, ip + d);
+						const uint32_t x = lds32u_a(cd_a + d) ^ lds32u_a(ip_a + d);
 						uint32_t mk = x ? d + ((uint32_t)(__ffs(x) - 1) >> 3) : 0x7fffffffu;
 						mk = g.min(min(mk, room));
 						if (mk < m + 4 * G) {
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 				uint32_t nb;
 				const uint32_t w = copy_piece(ip - cd, m, &nb);
 				const uint32_t lh = litlen ? litlen + 1 : 0;
-				const uint32_t lb = sin[next_emit + g.lane - 1];  // (lane 0 reads one byte below; unused)
+				const uint32_t lb = lds_u8(sin_a + next_emit + g.lane - 1);  // (lane 0 reads one byte below; unused)
 				uint32_t b = g.lane == 0 ? (litlen - 1) << 2 : lb;
 				if (g.lane >= lh)
 					b = w >> (8 * (g.lane - lh));
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 				op += lh + nb;
 			} else {
 				if (litlen)
-					op += emit_literal<G>(g, dst + op, sin, next_emit, litlen);
+					op += emit_literal<G>(g, dst + op, sin_a, next_emit, litlen);
 				op += emit_copy<G>(g, dst + op, ip - cd, m);
 			}
 			next_emit = ip + m;
@@ -337,33 +337,38 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 				fin = true;
 				break;
 			}
-			const uint32_t nl = next_emit - wbase;	// lane of the re-probe position, if still inside
+			// lane of the re-probe position if the parse can stay inside this window
+			const uint32_t nl = uni ? next_emit - wbase : 0x7fffffffu;
+			if (!exact) {
+				// lanes skipped by the copy never insert: undo (ip-1 = lane nl-1 stays, ip = lane nl goes on)
+				if (valid && g.lane > f && g.lane + 1 < nl)
+					sts_u16(slot, old);
+			} else {
+				fhit = f;
+			}
 			if (!multi || nl >= (uint32_t)G) {
 				wbase = next_emit - 1;
 				j0 = -2;
 				t = 1;
 				break;
 			}
-			// continue inside the window: lane nl-1 inserts ip-1, lane nl re-probes, scan restarts at nl+1
-			ins = nl - 1;
+			// continue inside the window: lane nl-1 inserted ip-1, lane nl re-probes, scan restarts at nl+1
 			cur = nl;
 			j0 = -(int)(nl + 1);
 		}
 		if (!fin) {
-			const bool mine = (I >> g.lane) & 1u;
-			if (!exact) {
-				if (valid && !mine)
-					tab[h] = (uint16_t)old;	 // undo the speculative insert
-			} else {
-				// the highest inserting lane of an equal-hash run owns the slot
+			if (exact) {
+				// the table is in its pre-window state: lanes up to the hit insert, the highest lane
+				// of an equal-hash run owns the slot
+				const unsigned I = fhit < 32 ? ((2u << fhit) - 1u) : 0xffffffffu;
 				const unsigned rivals = same & I & ~((2u << g.lane) - 1u);
-				if (valid && mine && !rivals)
-					tab[h] = (uint16_t)pp;
+				if (valid && ((I >> g.lane) & 1u) && !rivals)
+					sts_u16(slot, pp);
 			}
 			g.sync();
 		} else {
 			if (next_emit < n)
-				op += emit_literal<G>(g, dst + op, sin, next_emit, n - next_emit);
+				op += emit_literal<G>(g, dst + op, sin_a, next_emit, n - next_emit);
 			if (g.lane == 0)
 				a.out_len[blk] = op;
 			state = ST_NEED;

@@ -142,6 +142,22 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a)
 	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
 	return v;
 }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a)
+{
+	uint32_t v;
+	asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+	return v;
+}
+__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v)
+{
+	asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+// little-endian 32-bit load at an arbitrary shared BYTE address
+__device__ __forceinline__ uint32_t lds32u_a(uint32_t a)
+{
+	const uint32_t w = a & ~3u;
+	return __funnelshift_r(lds_u32(w), lds_u32(w + 4), (a & 3u) * 8u);
+}
 __device__ __forceinline__ uint2 lds_v2(uint32_t a)
 {
 	uint2 v;
