@@ -34,13 +34,14 @@ namespace csb {
 constexpr uint32_t kInPad = 48;	     // staging shift (< 16) + slack after the input for over-reads of the match extension
 constexpr uint32_t kTailMargin = 15; // kInputMarginBytes, csnappy_compress.c:468
 constexpr int kMaxThreads = 640;
+constexpr uint32_t kTokens = 32;     // deferred (literal, copy) tokens per group before a flush
 
 struct CompressParams {
 	csb_compress_args a;
 	uint32_t *counter;     // dynamic block claim
 	uint32_t table_bytes;  // 1 << wm
 	uint32_t in_area;      // bytes reserved for the staged input incl. pad (multiple of 16)
-	uint32_t group_smem;   // table_bytes + in_area + 16 (mbarrier)
+	uint32_t group_smem;   // table_bytes + in_area + 16 (mbarrier) + 8 * kTokens
 	uint32_t groups;       // groups per CTA that own shared memory
 };
 
@@ -132,6 +133,77 @@ __device__ __forceinline__ uint32_t emit_copy(const Group<G> &g, uint8_t *dst, u
 	return done + nb;
 }
 
+// ---- deferred emission ------------------------------------------------------------------------
+// The parse only records a token per match -- (next_emit | ip << 16, candidate | length << 16) --
+// and every kTokens matches the group emits them together: sizes in parallel, output offsets by a
+// shuffle scan, then every lane writes ITS token (literal header + payload + copy tag) on its own.
+// That replaces ~30 warp instructions per match in the serial chain by ~6 amortised ones.  Tokens
+// with a literal over 32 bytes or a copy over 64 bytes are written by the whole group instead.
+template <int G>
+__device__ __forceinline__ uint32_t flush_tokens(const Group<G> &g, uint8_t *dst, uint32_t op, uint32_t sin_a,
+						 uint32_t tok_a, uint32_t count)
+{
+	g.sync();
+	for (uint32_t base = 0; base < count; base += G) {
+		const uint32_t k = base + g.lane;
+		const bool have = k < count;
+		uint32_t ne = 0, litlen = 0, off = 1, m = 4;
+		if (have) {
+			const uint2 t = lds_v2(tok_a + 8 * k);
+			ne = t.x & 0xffffu;
+			litlen = (t.x >> 16) - ne;
+			off = (t.x >> 16) - (t.y & 0xffffu);
+			m = t.y >> 16;
+		}
+		const uint32_t hb = litlen == 0 ? 0u : (litlen <= 60 ? 1u : (litlen <= 256 ? 2u : 3u));
+		const uint32_t q = m >= 68 ? (m - 68) / 64 + 1 : 0;  // split rule, csnappy_compress.c:395-415
+		uint32_t rem = m - 64 * q;
+		const uint32_t n60 = rem > 64 ? 1u : 0u;
+		rem -= 60 * n60;
+		const uint32_t nbc = 3 * (q + n60) + ((rem < 12 && off < 2048) ? 2u : 3u);
+		const uint32_t size = have ? hb + litlen + nbc : 0u;
+		uint32_t incl = size;
+#pragma unroll
+		for (uint32_t d = 1; d < (uint32_t)G; d <<= 1) {
+			const uint32_t v = g.up(incl, d);
+			if (g.lane >= d)
+				incl += v;
+		}
+		const uint32_t at = op + incl - size;
+		const bool small = have && litlen <= 32 && m <= 64;
+		if (small) {
+			uint8_t *d = dst + at;
+			if (litlen) {
+				*d++ = (uint8_t)((litlen - 1) << 2);
+				const uint32_t from = sin_a + ne;
+				for (uint32_t i = 0; i < litlen; ++i)
+					d[i] = (uint8_t)lds_u8(from + i);
+				d += litlen;
+			}
+			uint32_t nb;
+			const uint32_t w = copy_piece(off, m, &nb);
+			d[0] = (uint8_t)w;
+			d[1] = (uint8_t)(w >> 8);
+			if (nb == 3)
+				d[2] = (uint8_t)(w >> 16);
+		}
+		unsigned big = g.ballot(have && !small);
+		while (big) {
+			const int kk = __ffs(big) - 1;
+			big &= big - 1;
+			const uint32_t bne = g.bcast(ne, kk), blit = g.bcast(litlen, kk), boff = g.bcast(off, kk);
+			const uint32_t bm = g.bcast(m, kk);
+			uint32_t o2 = g.bcast(at, kk);
+			if (blit)
+				o2 += emit_literal<G>(g, dst + o2, sin_a, bne, blit);
+			emit_copy<G>(g, dst + o2, boff, bm);
+		}
+		op += g.bcast(incl, G - 1);
+	}
+	g.sync();
+	return op;
+}
+
 // ---- the kernel ------------------------------------------------------------------------------
 
 enum : int { ST_NEED = 0, ST_LOADING = 1, ST_RUN = 2 };
@@ -150,7 +222,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 	uint8_t *sarea = gs + p.table_bytes;  // staged input, 16-byte aligned
 	const uint32_t sarea_a = smem_u32(sarea), tab_a = smem_u32(tab);
 	uint32_t sin_a = sarea_a;  // + (src & 15): shared address where the block's first byte lands
-	const uint32_t bar = smem_u32(sarea + p.in_area);
+	const uint32_t bar = smem_u32(sarea + p.in_area), tok_a = bar + 16;
 	const unsigned full = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
 
 	if (g.lane == 0) {
@@ -162,7 +234,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 	int state = ST_NEED;
 	uint32_t parity = 0;
 	// per-block state
-	uint32_t blk = 0, n = 0, ip_limit = 0, op = 0, next_emit = 0, wbase = 1, t = 0;
+	uint32_t blk = 0, n = 0, ip_limit = 0, op = 0, next_emit = 0, wbase = 1, t = 0, ntok = 0;
 	int shift = 0, j0 = 0;
 	uint8_t *dst = nullptr;
 
@@ -314,23 +386,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 					}
 				}
 			}
-			const uint32_t litlen = ip - next_emit;
-			if (m <= 64 && litlen <= (uint32_t)G - 4) {
-				// common case: literal (header + payload) and the copy tag leave in ONE store
-				uint32_t nb;
-				const uint32_t w = copy_piece(ip - cd, m, &nb);
-				const uint32_t lh = litlen ? litlen + 1 : 0;
-				const uint32_t lb = lds_u8(sin_a + next_emit + g.lane - 1);  // (lane 0 reads one byte below; unused)
-				uint32_t b = g.lane == 0 ? (litlen - 1) << 2 : lb;
-				if (g.lane >= lh)
-					b = w >> (8 * (g.lane - lh));
-				if (g.lane < lh + nb)
-					dst[op + g.lane] = (uint8_t)b;
-				op += lh + nb;
-			} else {
-				if (litlen)
-					op += emit_literal<G>(g, dst + op, sin_a, next_emit, litlen);
-				op += emit_copy<G>(g, dst + op, ip - cd, m);
+			// record the match; emission is deferred (flush_tokens)
+			sts_v2(tok_a + 8 * ntok, next_emit | (ip << 16), cd | (m << 16));
+			if (++ntok == kTokens) {
+				op = flush_tokens<G>(g, dst, op, sin_a, tok_a, ntok);
+				ntok = 0;
 			}
 			next_emit = ip + m;
 			if (next_emit >= ip_limit) {
@@ -367,6 +427,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 			}
 			g.sync();
 		} else {
+			if (ntok)
+				op = flush_tokens<G>(g, dst, op, sin_a, tok_a, ntok);
+			ntok = 0;
 			if (next_emit < n)
 				op += emit_literal<G>(g, dst + op, sin_a, next_emit, n - next_emit);
 			if (g.lane == 0)
@@ -409,7 +472,7 @@ extern "C" int csb_launch_compress(const struct csb_compress_args *a, csb_stream
 	if (in_cap > CSB_FRAGMENT_MAX)
 		in_cap = CSB_FRAGMENT_MAX;
 	p.in_area = ((in_cap + 15u) & ~15u) + kInPad;
-	p.group_smem = p.table_bytes + p.in_area + 16;
+	p.group_smem = p.table_bytes + p.in_area + 16 + 8 * kTokens;
 
 	const int G = a->lanes ? a->lanes : 32;
 	const int ctas_per_sm = a->ctas_per_sm > 0 ? a->ctas_per_sm : 1;

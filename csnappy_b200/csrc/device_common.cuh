@@ -30,6 +30,8 @@ struct Group {
 	__device__ __forceinline__ unsigned ballot(bool p) const { return __ballot_sync(mask, p) >> shift; }
 	template <typename T>
 	__device__ __forceinline__ T bcast(T v, int src) const { return __shfl_sync(mask, v, src, G); }
+	template <typename T>
+	__device__ __forceinline__ T up(T v, unsigned delta) const { return __shfl_up_sync(mask, v, delta, G); }
 	__device__ __forceinline__ unsigned match(unsigned key) const { return __match_any_sync(mask, key) >> shift; }
 	__device__ __forceinline__ unsigned min(unsigned v) const { return __reduce_min_sync(mask, v); }
 	__device__ __forceinline__ unsigned max(unsigned v) const { return __reduce_max_sync(mask, v); }
