@@ -175,6 +175,8 @@ def main():
     ap.add_argument("--lanes-c", type=int, default=0)
     ap.add_argument("--lanes-d", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--stage-d", type=int, default=0)
+    ap.add_argument("--smem-d", type=int, default=0)
     ap.add_argument("--only", default="", choices=["", "text", "zero", "random"],
                     help="diagnostic: make every page of one class (not the BASELINE workload)")
     args = ap.parse_args()
@@ -207,6 +209,10 @@ def main():
         cs.set_tuning("decompress_lanes", args.lanes_d)
     if args.ctas_per_sm:
         cs.set_tuning("ctas_per_sm", args.ctas_per_sm)
+    if args.stage_d:
+        cs.set_tuning("decompress_stage_input", args.stage_d)
+    if args.smem_d:
+        cs.set_tuning("decompress_smem_kb", args.smem_d)
 
     B = args.pages
     first, _ = shard.block_range(B * world, rank, world)  # weak scaling: rank r owns pages [r*B, (r+1)*B)

@@ -50,7 +50,7 @@ int csnappy_b200_device_ok(void)
 uint64_t csnappy_b200_kernel_launches(void) { return csb_launch_count(); }
 
 /* ---- tuning knobs ------------------------------------------------------- */
-static int g_compress_lanes, g_decompress_lanes, g_ctas_per_sm;
+static int g_compress_lanes, g_decompress_lanes, g_ctas_per_sm, g_stage_input, g_smem_kb;
 
 int csnappy_b200_set_tuning(const char *key, int value)
 {
@@ -63,6 +63,16 @@ int csnappy_b200_set_tuning(const char *key, int value)
 			g_compress_lanes = value;
 		else
 			g_decompress_lanes = value;
+		return 0;
+	}
+	if (!strcmp(key, "decompress_stage_input")) {
+		g_stage_input = value;
+		return 0;
+	}
+	if (!strcmp(key, "decompress_smem_kb")) {
+		if (value < 0 || value > 227)
+			return CSNAPPY_E_BAD_ARG;
+		g_smem_kb = value;
 		return 0;
 	}
 	if (!strcmp(key, "ctas_per_sm")) {
@@ -160,6 +170,8 @@ int csnappy_batch_decompress(const void *d_in, const uint64_t *d_in_off, uint64_
 	a.status = d_status;
 	a.flags = flags;
 	a.lanes = g_decompress_lanes;
+	a.stage_input = g_stage_input;
+	a.smem_kb = g_smem_kb;
 	a.ctas_per_sm = g_ctas_per_sm;
 	e = csb_launch_decompress(&a, (csb_stream_t)stream);
 	return e ? set_err("decompress launch", e) : 0;
@@ -376,6 +388,8 @@ static int decompress_host(const uint8_t *src, uint32_t src_len, uint8_t *dst, u
 	a.status = (int32_t *)(d_res + 1);
 	a.max_in_len = src_len;
 	a.lanes = g_decompress_lanes;
+	a.stage_input = g_stage_input;
+	a.smem_kb = g_smem_kb;
 	a.ctas_per_sm = g_ctas_per_sm;
 	TRY("decompress launch", csb_launch_decompress(&a, (csb_stream_t)s));
 	TRY("D2H result", cudaMemcpyAsync(&res, d_res, 8, cudaMemcpyDeviceToHost, s));
@@ -526,6 +540,8 @@ int csnappy_batch_decompress_host(const void *h_in, uint64_t in_stride, const ui
 		a.status = d_st;
 		a.flags = flags;
 		a.lanes = g_decompress_lanes;
+	a.stage_input = g_stage_input;
+	a.smem_kb = g_smem_kb;
 		a.ctas_per_sm = g_ctas_per_sm;
 		TRY("decompress launch", csb_launch_decompress(&a, (csb_stream_t)s));
 		TRY("D2H data", cudaMemcpyAsync((uint8_t *)h_out + done * out_stride, C.d_out2[k].p, nb * out_stride,
@@ -788,6 +804,8 @@ int csnappy_bc_decompress_host(const void *h_container, uint64_t container_lengt
 				a.flags = CSNAPPY_BATCH_RAW_IF_FULL;
 				a.max_in_len = longest;
 				a.lanes = g_decompress_lanes;
+	a.stage_input = g_stage_input;
+	a.smem_kb = g_smem_kb;
 				a.ctas_per_sm = g_ctas_per_sm;
 				TRY("decompress launch", csb_launch_decompress(&a, (csb_stream_t)b->s));
 				TRY("D2H pages", cudaMemcpyAsync((uint8_t *)h_out + done * page_size, b->d_out.p, (size_t)nb * page_size,

@@ -124,24 +124,72 @@ __device__ __forceinline__ int decode_streaming(const Group<G> &g, const uint8_t
 // Returns 1 when the stream is finished (rc says how), 0 to continue with the next batch.
 // gs = the group's shared memory; sin_off / sout_off = offsets of the staged input / output in it;
 // lut_a / meta_a = shared addresses of the walk table and of the group's G walk words + G descriptors.
-template <int G>
-__device__ __forceinline__ int decode_batch(const Group<G> &g, uint8_t *gs, uint32_t sin_off, uint32_t sout_off,
-					    uint32_t lut_a, uint32_t meta_a, uint32_t &st_pos, uint32_t &st_produced,
-					    int &st_irem, int &st_orem, int &rc)
+//
+// GIN = true: the compressed block is NOT staged; tag bytes, offsets and literal payloads are read
+// straight from global memory through L1 (ld.global.nc).  That halves the shared memory per block, so
+// almost twice as many blocks are in flight per SM -- the decoder is bound by the latency of its
+// serial chain, and more independent chains is what hides it.
+template <bool GIN>
+struct InBytes {
+	uint32_t sin_a;	     // shared address of the staged block (GIN = false)
+	const uint8_t *src;  // global address of the block (GIN = true)
+	__device__ __forceinline__ uint32_t u8(uint32_t pos) const
+	{
+		return GIN ? (uint32_t)__ldg(src + pos) : lds_u8(sin_a + pos);
+	}
+};
+
+// copy len input bytes at pos to shared address to_a with all lanes (long literals, stored blocks)
+template <int G, bool GIN>
+__device__ __forceinline__ void copy_in_to_shared(const Group<G> &g, const InBytes<GIN> &in, uint32_t pos, uint32_t to_a,
+						  uint32_t len)
 {
-	const uint8_t *sin = gs + sin_off;
-	const uint32_t gs_a = smem_u32(gs), sin_a = gs_a + sin_off, sout_a = gs_a + sout_off;
+	if (GIN) {
+		uint32_t i = g.lane;
+		for (; i + 3 * G < len; i += 4 * G) {
+			const uint32_t b0 = in.u8(pos + i), b1 = in.u8(pos + i + G), b2 = in.u8(pos + i + 2 * G),
+				       b3 = in.u8(pos + i + 3 * G);
+			sts_u8(to_a + i, b0);
+			sts_u8(to_a + i + G, b1);
+			sts_u8(to_a + i + 2 * G, b2);
+			sts_u8(to_a + i + 3 * G, b3);
+		}
+		for (; i < len; i += G)
+			sts_u8(to_a + i, in.u8(pos + i));
+	} else {
+		const uint32_t head = min((0u - to_a) & 3u, len);
+		if (g.lane < head)
+			sts_u8(to_a + g.lane, lds_u8(in.sin_a + pos + g.lane));
+		const uint32_t words = (len - head) >> 2;
+		for (uint32_t w = g.lane; w < words; w += G)
+			sts_u32(to_a + head + 4 * w, lds32u_a(in.sin_a + pos + head + 4 * w));
+		const uint32_t tail = head + (words << 2);
+		if (tail + g.lane < len)
+			sts_u8(to_a + tail + g.lane, lds_u8(in.sin_a + pos + tail + g.lane));
+	}
+}
+
+template <int G, bool GIN>
+__device__ __forceinline__ int decode_batch(const Group<G> &g, const InBytes<GIN> &in, uint32_t sout_a, uint32_t lut_a,
+					    uint32_t meta_a, uint32_t &st_pos, uint32_t &st_produced, int &st_irem,
+					    int &st_orem, int &rc)
+{
 	int irem = st_irem, orem = st_orem;
+	if (irem == 0) {  // end of input at a tag boundary
+		rc = E_OK;
+		return 1;
+	}
+	const uint32_t last = st_pos + (uint32_t)irem - 1;  // GIN: never read past the block
 	// ---- walk: positions and output offsets of up to G tags; ONE exit test per tag ----
 	// lut[tag] = input bytes of the whole tag | output bytes << 16; a long literal has 0xffff input
 	// bytes, so "input exhausted", "long literal", "payload cut off" and "no space" all show up as a
 	// negative remainder and are told apart once, after the loop.  pos | produced << 16 advances with
 	// one packed add.
-	uint32_t state = st_pos | (st_produced << 16), ra = sin_a + st_pos;
+	uint32_t state = st_pos | (st_produced << 16), ra = st_pos;
 	uint32_t k = 0, e = 0;
 #pragma unroll 8
 	for (; k < (uint32_t)G; ++k) {
-		e = lds_u32(lut_a + 4 * lds_u8(ra));
+		e = lds_u32(lut_a + 4 * in.u8(GIN ? min(ra, last) : ra));
 		sts_u32(meta_a + 4 * k, state);
 		const uint32_t adv = e & 0xffffu;
 		const int x = irem - (int)adv, y = orem - (int)(e >> 16);
@@ -169,35 +217,46 @@ __device__ __forceinline__ int decode_batch(const Group<G> &g, uint8_t *gs, uint
 	g.sync();
 
 	// ---- decode: lane k owns tag k (plus the tag that ran out of space: offset check only) ----
-	// descriptor: x = source shared address | len << 20 | overlap << 28, y = destination shared address | period << 20
-	uint32_t d0 = 0, d1 = 0;
-	bool bad = false;
+	// descriptor: x = source shared address | len << 20 | overlap << 28 | global literal << 29 | serial step << 30,
+	//             y = destination shared address | period << 20 | copy rounds of the step << 26
+	// Tags execute in STEPS of Q = G/8 consecutive tags, 8 lanes per tag, when no tag of the step reads
+	// what the step writes; such dependent steps (and overlapping copies) run one tag at a time.
+	constexpr uint32_t Q = G / 8;
+	uint32_t d0 = 0, d1 = 0, mylen = 0, myo = 0;
+	bool bad = false, dep = false, cp = false;
+	uint32_t src_end = 0;
 	if (g.lane < ntags + (werr == E_OUTPUT_OVERRUN ? 1u : 0u)) {
 		const uint32_t mp = lds_u32(meta_a + 4 * g.lane);
-		const uint32_t p = sin_a + (mp & 0xffffu), o = mp >> 16;
-		const uint32_t tag = lds_u8(p);
+		const uint32_t p = mp & 0xffffu, o = mp >> 16;
+		const uint32_t tag = in.u8(p);
 		const uint32_t kind = tag & 3u;
 		uint32_t len = (tag >> 2) + 1;
 		d1 = sout_a + o;
 		if (kind == 0) {
-			d0 = (p + 1) | (len << 20);  // literal: source is the input
+			// literal: source is the input (a shared address, or -- bit 29 -- a position in the global block)
+			d0 = (GIN ? (p + 1) | (1u << 29) : in.sin_a + p + 1) | (len << 20);
 		} else {
-			uint32_t off = lds_u8(p + 1);
+			uint32_t off = in.u8(p + 1);
 			if (kind == 1) {
 				len = ((tag >> 2) & 7u) + 4;
 				off |= (tag >> 5) << 8;
 			} else {
-				off |= lds_u8(p + 2) << 8;
+				off |= in.u8(p + 2) << 8;
 				if (kind == 3)
-					off |= (lds_u8(p + 3) << 16) | (lds_u8(p + 4) << 24);
+					off |= (in.u8(p + 3) << 16) | (in.u8(p + 4) << 24);
 			}
 			bad = off - 1u >= o;  // off == 0 or off > produced, csnappy_decompress.c:302
 			d0 = ((d1 - off) & 0xfffffu) | (len << 20);
+			cp = true;
+			src_end = o - off + len;
 			if (off < len) {  // overlapping: mode bit + the period
 				d0 |= 1u << 28;
 				d1 |= off << 20;
+				dep = true;
 			}
 		}
+		mylen = g.lane < ntags ? len : 0u;
+		myo = o;
 	}
 	const unsigned badmask = g.ballot(bad);
 	if (badmask || werr != E_OK) {
@@ -205,47 +264,84 @@ __device__ __forceinline__ int decode_batch(const Group<G> &g, uint8_t *gs, uint
 		rc = badmask ? E_DATA_MALFORMED : werr;
 		return 1;
 	}
+	if (Q > 1) {
+		// a copy whose source reaches into the output of its own step makes the step serial
+		const uint32_t first = g.lane & ~(Q - 1);
+		const uint32_t o_first = g.bcast(myo, (int)first);
+		dep = dep || (cp && g.lane < ntags && src_end > o_first);
+		const unsigned dm = g.ballot(dep);
+		uint32_t smax = mylen;
+#pragma unroll
+		for (uint32_t x = 1; x < Q; x <<= 1)
+			smax = max(smax, __shfl_xor_sync(g.mask, smax, x, G));
+		if ((dm >> first) & ((1u << Q) - 1u))
+			d0 |= 1u << 30;
+		d1 |= ((smax + 7) >> 3) << 26;
+	}
 	const uint32_t desc_a = meta_a + 4 * G;
 	sts_v2(desc_a + 8 * g.lane, d0, d1);
 	g.sync();
 
-	// ---- execute in stream order, all lanes moving bytes ----
-	for (uint32_t t = 0; t < ntags; ++t) {
-		const uint2 d = lds_v2(desc_a + 8 * t);
-		const uint32_t from = (d.x & 0xfffffu) + g.lane, to = (d.y & 0xfffffu) + g.lane;
-		const uint32_t len = (d.x >> 20) & 0xffu;
-		if (d.x < (1u << 28)) {
-			// literal or disjoint copy (len <= 64): at most 64 / G predicated rounds, no loop
-#pragma unroll
-			for (uint32_t j = 0; j < 64u / G; ++j)
-				if (g.lane + j * G < len)
-					sts_u8(to + j * G, lds_u8(from + j * G));
-		} else {
-			const uint32_t off = d.y >> 20;
-			if (off == 1) {
-				const uint32_t v = lds_u8(from - g.lane);
-				for (uint32_t i = g.lane; i < len; i += G)
-					sts_u8(to + i - g.lane, v);
-			} else if (off >= (uint32_t)G) {
-				// a round of G bytes only reads what earlier rounds wrote
-				for (uint32_t c = 0; c < len; c += G) {
-					if (c + g.lane < len)
-						sts_u8(to + c, lds_u8(from + c));
-					g.sync();
-				}
-			} else {
-				// short period: byte i repeats the pattern [o - off, o)
-				for (uint32_t i = g.lane; i < len; i += G)
-					sts_u8(to + i - g.lane, lds_u8(from - g.lane + i % off));
+	// ---- execute in stream order ----
+	const uint32_t sub = g.lane & 7u, tq = g.lane >> 3;
+	for (uint32_t t = 0; t < ntags; t += Q) {
+		if (Q > 1) {
+			const uint2 d = lds_v2(desc_a + 8 * (t + tq));
+			if (!(d.x & (1u << 30))) {
+				// independent step: 8 lanes per tag, all Q tags at once
+				const uint32_t from = (d.x & 0xfffffu) + sub, to = (d.y & 0xfffffu) + sub;
+				const uint32_t len = (d.x >> 20) & 0xffu, rounds = (d.y >> 26) & 0xfu;
+				for (uint32_t j = 0; j < rounds; ++j)
+					if (sub + 8 * j < len)
+						sts_u8(to + 8 * j, (GIN && (d.x & (1u << 29))) ? in.u8(from + 8 * j) : lds_u8(from + 8 * j));
+				g.sync();
+				continue;
 			}
 		}
-		g.sync();
+		const uint32_t t_end = min(t + Q, ntags);
+		for (uint32_t u = t; u < t_end; ++u) {
+			const uint2 d = lds_v2(desc_a + 8 * u);
+			const uint32_t from = (d.x & 0xfffffu) + g.lane, to = (d.y & 0xfffffu) + g.lane;
+			const uint32_t len = (d.x >> 20) & 0xffu;
+			if (!(d.x & (3u << 28))) {
+				// literal or disjoint copy (len <= 64): at most 64 / G predicated rounds, no loop
+#pragma unroll
+				for (uint32_t j = 0; j < 64u / G; ++j)
+					if (g.lane + j * G < len)
+						sts_u8(to + j * G, lds_u8(from + j * G));
+			} else if (GIN && (d.x & (1u << 29))) {
+				// literal from the global block
+#pragma unroll
+				for (uint32_t j = 0; j < 64u / G; ++j)
+					if (g.lane + j * G < len)
+						sts_u8(to + j * G, in.u8(from + j * G));
+			} else {
+				const uint32_t off = (d.y >> 20) & 0x3fu;
+				if (off == 1) {
+					const uint32_t v = lds_u8(from - g.lane);
+					for (uint32_t i = g.lane; i < len; i += G)
+						sts_u8(to + i - g.lane, v);
+				} else if (off >= (uint32_t)G) {
+					// a round of G bytes only reads what earlier rounds wrote
+					for (uint32_t c = 0; c < len; c += G) {
+						if (c + g.lane < len)
+							sts_u8(to + c, lds_u8(from + c));
+						g.sync();
+					}
+				} else {
+					// short period: byte i repeats the pattern [o - off, o)
+					for (uint32_t i = g.lane; i < len; i += G)
+						sts_u8(to + i - g.lane, lds_u8(from - g.lane + i % off));
+				}
+			}
+			g.sync();
+		}
 	}
 
 	// ---- a long literal (61+ bytes, 1-4 length bytes) ends the batch and is copied by all lanes ----
 	if (longlit) {
 		const uint32_t ilen = pos + (uint32_t)irem;
-		const uint32_t tag = sin[pos++];
+		const uint32_t tag = in.u8(pos++);
 		const uint32_t nb = (tag >> 2) + 1 - 60;
 		if (ilen - pos < nb) {
 			rc = E_DATA_MALFORMED;
@@ -253,7 +349,7 @@ __device__ __forceinline__ int decode_batch(const Group<G> &g, uint8_t *gs, uint
 		}
 		uint32_t v = 0;
 		for (uint32_t b = 0; b < nb; ++b)
-			v |= (uint32_t)sin[pos + b] << (8 * b);
+			v |= in.u8(pos + b) << (8 * b);
 		pos += nb;
 		const uint32_t len = v + 1;  // 0xffffffff wraps to a zero-length literal (csnappy_decompress.c:370)
 		// (a length of 2^31 or more passes the reference's signed input check and fails on space, :374)
@@ -265,17 +361,7 @@ __device__ __forceinline__ int decode_batch(const Group<G> &g, uint8_t *gs, uint
 			rc = E_OUTPUT_OVERRUN;
 			return 1;
 		}
-		uint8_t *to = gs + sout_off + produced;
-		const uint32_t head = min((uint32_t)(-(intptr_t)to) & 3u, len);
-		if (g.lane < head)
-			to[g.lane] = sin[pos + g.lane];
-		const uint32_t words = (len - head) >> 2;
-		uint32_t *tw = reinterpret_cast<uint32_t *>(to + head);
-		for (uint32_t w = g.lane; w < words; w += G)
-			tw[w] = lds32u(sin, pos + head + 4 * w);
-		const uint32_t tail = head + (words << 2);
-		if (tail + g.lane < len)
-			to[tail + g.lane] = sin[pos + tail + g.lane];
+		copy_in_to_shared<G, GIN>(g, in, pos, sout_a + produced, len);
 		pos += len;
 		produced += len;
 		irem = (int)(ilen - pos);
@@ -295,7 +381,7 @@ __device__ __forceinline__ int decode_batch(const Group<G> &g, uint8_t *gs, uint
 
 enum : int { DS_NEED = 0, DS_LOADING = 1, DS_RUN = 2 };
 
-template <int G>
+template <int G, bool GIN>
 __global__ void __launch_bounds__(kMaxThreadsD, 1) decompress_kernel(const DecompressParams p)
 {
 	extern __shared__ __align__(128) uint8_t smem[];
@@ -335,7 +421,10 @@ __global__ void __launch_bounds__(kMaxThreadsD, 1) decompress_kernel(const Decom
 	uint32_t parity = 0, blk = 0;
 	uint32_t st_pos = 0, st_produced = 0;  // input / output cursor of the staged block
 	int st_irem = 0, st_orem = 0;	       // input bytes left, output capacity left
-	uint32_t sin_off = 0;
+	InBytes<GIN> in;
+	in.sin_a = smem_u32(gs);
+	in.src = nullptr;
+	const uint32_t sout_a = smem_u32(sout);
 	bool raw = false;
 	uint8_t *dst = nullptr;
 
@@ -372,7 +461,7 @@ __global__ void __launch_bounds__(kMaxThreadsD, 1) decompress_kernel(const Decom
 					ilen -= used;
 				}
 			}
-			if (rc == E_OK && !(ilen + 32 <= p.in_area && cap <= p.out_area)) {
+			if (rc == E_OK && !((GIN || ilen + 32 <= p.in_area) && cap <= p.out_area && ilen < 65536u)) {
 				uint32_t produced = 0;
 				if ((a.flags & 4u) && ilen == cap) {  // stored block too large to stage: plain copy
 					for (uint32_t i = g.lane; i < ilen; i += G)
@@ -403,9 +492,14 @@ __global__ void __launch_bounds__(kMaxThreadsD, 1) decompress_kernel(const Decom
 			st_irem = (int)ilen;
 			st_orem = (int)cap;
 			raw = (a.flags & 4u) && ilen == cap;  // stored block (block_compressor.c:378)
-			bool bulk;
-			sin_off = stage_block<G>(g, gs, src, ilen, bar, &bulk);
-			state = bulk ? DS_LOADING : DS_RUN;
+			if (GIN) {
+				in.src = src;
+				state = DS_RUN;
+			} else {
+				bool bulk;
+				in.sin_a = smem_u32(gs) + stage_block<G>(g, gs, src, ilen, bar, &bulk);
+				state = bulk ? DS_LOADING : DS_RUN;
+			}
 			g.sync();
 		}
 		if (state == DS_LOADING) {
@@ -417,19 +511,11 @@ __global__ void __launch_bounds__(kMaxThreadsD, 1) decompress_kernel(const Decom
 
 		int rc = E_OK;
 		if (raw) {
-			// stored block: realign the staged bytes into the output area, 16 bytes per lane
-			const uint32_t n = (uint32_t)st_irem;
-			for (uint32_t c = 16 * g.lane; c < n; c += 16 * G) {
-				uint4 v;
-				v.x = lds32u(gs, sin_off + c);
-				v.y = lds32u(gs, sin_off + c + 4);
-				v.z = lds32u(gs, sin_off + c + 8);
-				v.w = lds32u(gs, sin_off + c + 12);
-				*reinterpret_cast<uint4 *>(sout + c) = v;
-			}
-			st_produced = n;
+			// stored block: plain copy into the output area
+			copy_in_to_shared<G, GIN>(g, in, 0, sout_a, (uint32_t)st_irem);
+			st_produced = (uint32_t)st_irem;
 			g.sync();
-		} else if (!decode_batch<G>(g, gs, sin_off, p.in_area, lut_a, meta_a, st_pos, st_produced, st_irem, st_orem, rc)) {
+		} else if (!decode_batch<G, GIN>(g, in, sout_a, lut_a, meta_a, st_pos, st_produced, st_irem, st_orem, rc)) {
 			continue;
 		}
 
@@ -468,15 +554,27 @@ __global__ void __launch_bounds__(kMaxThreadsD, 1) decompress_kernel(const Decom
 
 using namespace csb;
 
-template <int G>
-static int launch_decompress_g(const DecompressParams &p, int threads, int ctas, size_t smem, cudaStream_t s)
+template <int G, bool GIN>
+static int launch_decompress_gi(const DecompressParams &p, int threads, int ctas, size_t smem, cudaStream_t s)
 {
-	cudaError_t e = cudaFuncSetAttribute(decompress_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	cudaError_t e = cudaFuncSetAttribute(decompress_kernel<G, GIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess)
 		return (int)e;
-	decompress_kernel<G><<<ctas, threads, smem, s>>>(p);
+	// leave the rest of the unified array to L1: the unstaged input is read through it
+	e = cudaFuncSetAttribute(decompress_kernel<G, GIN>, cudaFuncAttributePreferredSharedMemoryCarveout,
+				 (int)((smem + 2048) * 100 / (228 * 1024) + 1));
+	if (e != cudaSuccess)
+		return (int)e;
+	decompress_kernel<G, GIN><<<ctas, threads, smem, s>>>(p);
 	count_launch();
 	return (int)cudaGetLastError();
+}
+
+template <int G>
+static int launch_decompress_g(const DecompressParams &p, bool gin, int threads, int ctas, size_t smem, cudaStream_t s)
+{
+	return gin ? launch_decompress_gi<G, true>(p, threads, ctas, smem, s)
+		   : launch_decompress_gi<G, false>(p, threads, ctas, smem, s);
 }
 
 extern "C" int csb_launch_decompress(const struct csb_decompress_args *a, csb_stream_t s)
@@ -504,13 +602,20 @@ extern "C" int csb_launch_decompress(const struct csb_decompress_args *a, csb_st
 	}
 	if (in_cap > 32 + CSB_FRAGMENT_MAX + CSB_FRAGMENT_MAX / 6)
 		in_cap = 32 + CSB_FRAGMENT_MAX + CSB_FRAGMENT_MAX / 6;
-	p.in_area = (uint32_t)((in_cap + 15) & ~15ull) + 32;  // + staging shift (< 16) + slack for over-reads
+	const bool gin = a->stage_input == 2;  // 2: read the compressed block through L1 instead of staging it (measured slower)
+	p.in_area = gin ? 0u : (uint32_t)((in_cap + 15) & ~15ull) + 32;  // + staging shift (< 16) + slack for over-reads
 	p.out_area = (uint32_t)((out_cap + 15) & ~15ull);
 	const uint32_t meta_bytes = 12u * (uint32_t)G + 16u;  // walk words, descriptors, mbarrier
 	p.group_smem = p.in_area + p.out_area + meta_bytes;
 
 	const int ctas_per_sm = a->ctas_per_sm > 0 ? a->ctas_per_sm : 1;
 	long budget = (long)di.smem_per_sm / ctas_per_sm - 1024 - 1024;  // 1024: the static walk table
+	if (gin) {
+		// keep part of the unified L1/shared array as L1 for the input stream
+		const long cap_kb = a->smem_kb > 0 ? a->smem_kb : 164;
+		if (budget > cap_kb * 1024 / ctas_per_sm)
+			budget = cap_kb * 1024 / ctas_per_sm;
+	}
 	if (budget > di.smem_per_block_optin - 1024)
 		budget = di.smem_per_block_optin - 1024;
 	int groups = (int)(budget / p.group_smem);
@@ -545,9 +650,9 @@ extern "C" int csb_launch_decompress(const struct csb_decompress_args *a, csb_st
 		return (int)ce;
 	p.counter = counter;
 	switch (G) {
-	case 32: e = launch_decompress_g<32>(p, threads, (int)ctas, smem, s); break;
-	case 16: e = launch_decompress_g<16>(p, threads, (int)ctas, smem, s); break;
-	case 8: e = launch_decompress_g<8>(p, threads, (int)ctas, smem, s); break;
+	case 32: e = launch_decompress_g<32>(p, gin, threads, (int)ctas, smem, s); break;
+	case 16: e = launch_decompress_g<16>(p, gin, threads, (int)ctas, smem, s); break;
+	case 8: e = launch_decompress_g<8>(p, gin, threads, (int)ctas, smem, s); break;
 	default: e = (int)cudaErrorInvalidValue; break;
 	}
 	cudaFreeAsync(counter, s);

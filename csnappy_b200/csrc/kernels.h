@@ -48,6 +48,8 @@ struct csb_decompress_args {
 	uint32_t max_in_len;	/* staging hint: longest input block (0 = derive) */
 	int lanes;
 	int ctas_per_sm;
+	int stage_input;	/* 2: read the compressed block through L1; else stage it in shared memory */
+	int smem_kb;		/* unstaged mode: shared memory to use per SM, rest stays L1 (0 = default) */
 };
 
 /* all return 0 or a cudaError_t value (> 0) */

@@ -187,8 +187,9 @@ def test_batch_compress_shrink_table_flag(cs, chk):
         assert got == chk.compress_fragment(text[:n], oracle.port().chunk_wm(n, 16)), n
 
 
+@pytest.mark.parametrize("stage", [0, 2])
 @pytest.mark.parametrize("lanes", [32, 16, 8])
-def test_batch_decompress_roundtrip_and_errors(cs, chk, lanes):
+def test_batch_decompress_roundtrip_and_errors(cs, chk, lanes, stage):
     pages = fuzz_pages(99, 140, 4096)
     comp = [chk.compress_fragment(p, 13) for p in pages]
     rng = np.random.default_rng(5)
@@ -207,12 +208,14 @@ def test_batch_decompress_roundtrip_and_errors(cs, chk, lanes):
     d_in, d_len, _, _ = _to_dev(streams, stride)
     d_caps = torch.tensor(caps, dtype=torch.int32).cuda()
     cs.set_tuning("decompress_lanes", lanes)
+    cs.set_tuning("decompress_stage_input", stage)
     try:
         out, out_len, status = cs.batch_decompress(d_in, d_len, len(streams), 4096, in_stride=stride, out_caps=d_caps,
                                                    out_stride=4096)
         torch.cuda.synchronize()
     finally:
         cs.set_tuning("decompress_lanes", 0)
+        cs.set_tuning("decompress_stage_input", 0)
     o, ol, st = out.cpu().numpy(), out_len.cpu().numpy(), status.cpu().numpy()
     n_err = 0
     for i, s in enumerate(streams):
