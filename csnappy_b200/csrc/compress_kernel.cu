@@ -320,15 +320,38 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 		if (valid)
 			sts_u16(slot, pp);
 		g.sync();
-		const bool exact = g.ballot(valid && lds_u16(slot) != pp) != 0;  // two lanes share a slot
+		const uint32_t rb1 = lds_u16(slot);
+		const bool lost = valid && rb1 != pp;
+		const bool exact = g.ballot(lost) != 0;	 // two lanes share a slot
 		// candidate: the table -- or, with shared slots, the latest lower lane with the same hash
 		// (invalid lanes must not follow a stale entry: blocks under 15 bytes never clear the table)
 		uint32_t cand = valid ? old : 0u;
 		unsigned same = 0;
 		if (exact) {
+			// Who shares a slot with whom?  For the common case of PAIRS in a window of consecutive
+			// positions a second insert + readback answers it (the loser of the first round saw the
+			// winner's position; after the losers insert, the winner sees its loser); three or more
+			// lanes on one slot, or a strided window, fall back to match.any (slow: ~300 cycles).
+			bool paired = false;
+			if (uni) {
+				g.sync();
+				if (lost)
+					sts_u16(slot, pp);
+				g.sync();
+				const uint32_t rb2 = lds_u16(slot);
+				if (!g.ballot(lost && rb2 != pp)) {
+					paired = true;
+					const uint32_t q = lost ? rb1 : rb2;  // the partner's position (own position: none)
+					same = 1u << g.lane;
+					if (valid && q != pp)
+						same |= 1u << (q - wbase);
+				}
+				g.sync();
+			}
 			if (valid)
 				sts_u16(slot, old);  // back to the state before this window
-			same = g.match(valid ? slot : (0x80000000u | g.lane));
+			if (!paired)
+				same = g.match(valid ? slot : (0x80000000u | g.lane));
 			const unsigned lower = same & ((1u << g.lane) - 1u);
 			const uint32_t lp = g.bcast(pp, lower ? 31 - __clz(lower) : (int)g.lane);
 			if (lower)

@@ -1,0 +1,39 @@
+#!/usr/bin/env python
+"""Small end-to-end run for compute-sanitizer (memcheck / racecheck / synccheck):
+    compute-sanitizer --tool racecheck python tools/sanitize_run.py
+"""
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, ".")
+sys.path.insert(0, "tests")
+import csnappy_b200 as cs
+from cases import fuzz_pages
+from csnappy_b200 import synth
+
+B, L = 96, 4096
+pages = synth.mixed_pages(B, L, seed=0x5EED0001, device="cuda", pool_bytes=1 << 20)
+extra = torch.from_numpy(np.frombuffer(b"".join(fuzz_pages(5, 28, L)), dtype=np.uint8).copy()).cuda()
+pages = torch.cat([pages, extra])
+B = pages.numel() // L
+for lanes in (32, 16, 8):
+    cs.set_tuning("compress_lanes", lanes)
+    cs.set_tuning("decompress_lanes", lanes)
+    out, out_len = cs.batch_compress_fragments(pages, L, B, 13)
+    ostride = cs.api.out_stride_for(L)
+    back, back_len, status = cs.batch_decompress(out, out_len, B, L, in_stride=ostride)
+    torch.cuda.synchronize()
+    assert int((status != 0).sum()) == 0 and torch.equal(back.view(B, L), pages.view(B, L)), lanes
+    packed, off = cs.batch_pack(out, ostride, out_len, B)
+    back2, _, st2 = cs.batch_decompress(packed, out_len, B, L, in_off=off[:-1].contiguous())
+    torch.cuda.synchronize()
+    assert int((st2 != 0).sum()) == 0 and torch.equal(back2.view(B, L), pages.view(B, L)), lanes
+# 32 KiB fragments
+frag = synth.text_fragments(6, 32768, device="cuda", pool_bytes=1 << 20)
+o, ol = cs.batch_compress_fragments(frag, 32768, 6, 15)
+b, bl, st = cs.batch_decompress(o, ol, 6, 32768, in_stride=cs.api.out_stride_for(32768))
+torch.cuda.synchronize()
+assert int((st != 0).sum()) == 0 and torch.equal(b.view(6, 32768), frag.view(6, 32768))
+print("sanitize_run ok")
