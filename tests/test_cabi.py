@@ -93,3 +93,22 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".c", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "import oracle" not in text and "liboracle" not in text and "snappy_oracle" not in text, f
+
+
+C_MAIN = os.path.join(ROOT, "tests", "c", "dropin_main.c")
+
+
+def build_c_caller(tmpdir) -> str:
+    """A plain C program built only against include/ and linked against the library,
+    like the reference's own callers (cl_tester, block_compressor, the zram glue)."""
+    from csnappy_b200._lib import LIB_PATH
+
+    exe = os.path.join(str(tmpdir), "dropin_main")
+    libdir = os.path.dirname(LIB_PATH)
+    subprocess.run(["gcc", "-std=gnu99", "-Wall", "-Wextra", "-Werror", "-O2", "-I" + os.path.join(ROOT, "include"),
+                    "-o", exe, C_MAIN, "-L" + libdir, "-lcsnappy_b200", "-Wl,-rpath," + libdir], check=True)
+    return exe
+
+
+def test_c_caller_compiles_and_links(lib, tmp_path):
+    assert os.path.exists(build_c_caller(tmp_path))

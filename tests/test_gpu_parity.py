@@ -275,6 +275,20 @@ def test_batch_pack(cs):
         assert (p[off[i]: off[i] + lens[i]] == slots[i, : lens[i]]).all(), i
 
 
+def test_c_caller_through_the_plain_c_abi(cs, urls, urls_snappy, tmp_path):
+    """tests/c/dropin_main.c: cl_tester / zram / block_compressor style calls from C."""
+    import subprocess
+
+    from test_cabi import build_c_caller
+
+    exe = build_c_caller(tmp_path)
+    a, b = tmp_path / "urls.10K", tmp_path / "urls.10K.snappy"
+    a.write_bytes(urls)
+    b.write_bytes(urls_snappy)
+    r = subprocess.run([exe, str(a), str(b)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "dropin ok" in r.stdout, r.stdout + r.stderr
+
+
 # --------------------------------------------------------------------------- block_compressor container
 def _ref_container(chk, data: bytes, page: int, wm: int) -> bytes:
     """block_compressor.c:275-345 restated with the oracle as the page compressor."""
