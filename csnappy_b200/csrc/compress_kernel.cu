@@ -523,8 +523,10 @@ extern "C" int csb_launch_compress(const struct csb_compress_args *a, csb_stream
 	const int threads = (groups * G + 31) / 32 * 32;  // whole warps; surplus lanes exit at once
 	const size_t smem = (size_t)groups * p.group_smem;
 
-	uint32_t *counter = nullptr;
-	cudaError_t ce = cudaMallocAsync((void **)&counter, sizeof(uint32_t), s);
+	uint32_t *counter = a->counter;
+	cudaError_t ce = cudaSuccess;
+	if (!counter)
+		ce = cudaMallocAsync((void **)&counter, sizeof(uint32_t), s);
 	if (ce != cudaSuccess)
 		return (int)ce;
 	ce = cudaMemsetAsync(counter, 0, sizeof(uint32_t), s);
@@ -537,6 +539,7 @@ extern "C" int csb_launch_compress(const struct csb_compress_args *a, csb_stream
 	case 8: e = launch_compress_g<8>(p, threads, (int)ctas, smem, s); break;
 	default: e = (int)cudaErrorInvalidValue; break;
 	}
-	cudaFreeAsync(counter, s);
+	if (!a->counter)
+		cudaFreeAsync(counter, s);
 	return e;
 }

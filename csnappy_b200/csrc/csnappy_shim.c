@@ -574,7 +574,7 @@ out:
 struct bc_slot {
 	cudaStream_t s;
 	cudaEvent_t ev;
-	struct buf d_in, d_slots, d_len, d_clen, d_off, d_packed, d_out, d_res;
+	struct buf d_in, d_slots, d_len, d_clen, d_off, d_packed, d_out, d_res, d_ctr;
 	struct buf h_res; /* pinned: [u64 total] or [u32 out_len[n]][i32 status[n]] */
 	int busy;
 	uint64_t first;
@@ -654,6 +654,7 @@ int csnappy_bc_compress_host(const void *h_in, uint64_t input_length, uint32_t p
 		TRY("cudaMalloc(off)", grow_dev(&b->d_off, ((size_t)chunk + 1) * 8 + 64));
 		TRY("cudaMalloc(packed)", grow_dev(&b->d_packed, (size_t)chunk * page_size + 64));
 		TRY("cudaMallocHost(res)", grow_pin(&b->h_res, 64));
+		TRY("cudaMalloc(ctr)", grow_dev(&b->d_ctr, 64));
 		b->busy = 0;
 	}
 	for (done = 0; done < nr || retire_next < issued;) {
@@ -688,6 +689,7 @@ int csnappy_bc_compress_host(const void *h_in, uint64_t input_length, uint32_t p
 			a.wm = workmem_bytes_power_of_two;
 			a.lanes = g_compress_lanes;
 			a.ctas_per_sm = g_ctas_per_sm;
+			a.counter = (uint32_t *)b->d_ctr.p;
 			TRY("compress launch", csb_launch_compress(&a, (csb_stream_t)b->s));
 			TRY("pack launch", csb_launch_pack_stored((const uint8_t *)b->d_slots.p, out_stride, (const uint32_t *)b->d_len.p, nb,
 								  (const uint8_t *)b->d_in.p, page_size, in_bytes, (uint32_t *)b->d_clen.p,
@@ -746,6 +748,7 @@ int csnappy_bc_decompress_host(const void *h_container, uint64_t container_lengt
 		TRY("cudaMalloc(out)", grow_dev(&b->d_out, (size_t)chunk * page_size + 64));
 		TRY("cudaMalloc(res)", grow_dev(&b->d_res, (size_t)chunk * 8 + 64));
 		TRY("cudaMallocHost(res)", grow_pin(&b->h_res, (size_t)chunk * 8 + 64));
+		TRY("cudaMalloc(ctr)", grow_dev(&b->d_ctr, 64));
 		b->busy = 0;
 	}
 	for (done = 0; done < nr || retire_next < issued;) {
@@ -803,6 +806,7 @@ int csnappy_bc_decompress_host(const void *h_container, uint64_t container_lengt
 				a.status = (int32_t *)b->d_res.p + nb;
 				a.flags = CSNAPPY_BATCH_RAW_IF_FULL;
 				a.max_in_len = longest;
+				a.counter = (uint32_t *)b->d_ctr.p;
 				a.lanes = g_decompress_lanes;
 	a.stage_input = g_stage_input;
 	a.smem_kb = g_smem_kb;

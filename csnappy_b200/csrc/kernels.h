@@ -30,6 +30,7 @@ struct csb_compress_args {
 	uint32_t flags;		/* CSNAPPY_BATCH_SHRINK_TABLE */
 	int lanes;		/* lanes cooperating on one block: 8, 16, 32 (0 = default) */
 	int ctas_per_sm;	/* 0 = default */
+	uint32_t *counter;	/* device word for the block claim counter (NULL: stream-ordered allocation per launch) */
 };
 
 struct csb_decompress_args {
@@ -48,6 +49,7 @@ struct csb_decompress_args {
 	uint32_t max_in_len;	/* staging hint: longest input block (0 = derive) */
 	int lanes;
 	int ctas_per_sm;
+	uint32_t *counter;	/* device word for the block claim counter (NULL: stream-ordered allocation per launch) */
 	int stage_input;	/* 2: read the compressed block through L1; else stage it in shared memory */
 	int smem_kb;		/* unstaged mode: shared memory to use per SM, rest stays L1 (0 = default) */
 };
