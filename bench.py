@@ -343,7 +343,10 @@ def main():
             "roofline": {"kernel": f"{dominant}_kernel", "bound": "hbm",
                          "achieved": round(ach_c if dominant == "compress" else ach_d, 2), "peak": peak,
                          "unit": "GB/s", "frac": round((ach_c if dominant == "compress" else ach_d) / peak, 4),
-                         "traffic": (traffic or {}).get(dominant), "peak_source": peak_src,
+                         "traffic": (int((traffic or {}).get(dominant) * B / traffic["pages"]) if traffic else None),
+                         "traffic_source": ("profiles/traffic.json: ncu dram bytes of one launch at "
+                                            f"{traffic['pages']} pages, scaled to this batch") if traffic else None,
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(alg_c if dominant == "compress" else alg_d),
                          "kernel_ms": round(tc_ms if dominant == "compress" else td_ms, 3)},
             "roofline_other": {"kernel": ("decompress" if dominant == "compress" else "compress") + "_kernel",
