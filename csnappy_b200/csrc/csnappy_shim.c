@@ -200,8 +200,8 @@ static struct {
 	cudaStream_t stream[3];
 	struct buf d_in, d_out, d_aux, d_pack; /* device */
 	struct buf h_pin;		       /* pinned host bounce buffer */
-	struct buf d_in2[3], d_out2[3], d_aux2[3];
-} C = {PTHREAD_MUTEX_INITIALIZER};
+	struct buf d_in2[3], d_out2[3], d_aux2[3], d_ctr2[3], d_ctr;
+} C = {.mu = PTHREAD_MUTEX_INITIALIZER};
 
 static int ctx_init(void)
 {
@@ -464,6 +464,7 @@ int csnappy_batch_compress_fragments_host(const void *h_in, uint64_t in_stride, 
 		TRY("cudaMalloc(in)", grow_dev(&C.d_in2[k], chunk * in_stride + 64));
 		TRY("cudaMalloc(out)", grow_dev(&C.d_out2[k], chunk * out_stride + 64));
 		TRY("cudaMalloc(len)", grow_dev(&C.d_aux2[k], chunk * 4 + 64));
+		TRY("cudaMalloc(ctr)", grow_dev(&C.d_ctr2[k], 64));
 	}
 	for (done = 0, k = 0; done < n_blocks; done += chunk, k = (k + 1) % NPIPE) {
 		size_t nb = n_blocks - done < chunk ? n_blocks - done : chunk;
@@ -482,6 +483,7 @@ int csnappy_batch_compress_fragments_host(const void *h_in, uint64_t in_stride, 
 		a.wm = workmem_bytes_power_of_two;
 		a.lanes = g_compress_lanes;
 		a.ctas_per_sm = g_ctas_per_sm;
+		a.counter = (uint32_t *)C.d_ctr2[k].p;
 		TRY("compress launch", csb_launch_compress(&a, (csb_stream_t)s));
 		TRY("D2H data", cudaMemcpyAsync((uint8_t *)h_out + done * out_stride, C.d_out2[k].p, nb * out_stride,
 						cudaMemcpyDeviceToHost, s));
@@ -518,6 +520,7 @@ int csnappy_batch_decompress_host(const void *h_in, uint64_t in_stride, const ui
 		TRY("cudaMalloc(in)", grow_dev(&C.d_in2[k], chunk * in_stride + 64));
 		TRY("cudaMalloc(out)", grow_dev(&C.d_out2[k], chunk * out_stride + 64));
 		TRY("cudaMalloc(aux)", grow_dev(&C.d_aux2[k], chunk * 12 + 64));
+		TRY("cudaMalloc(ctr)", grow_dev(&C.d_ctr2[k], 64));
 	}
 	for (done = 0, k = 0; done < n_blocks; done += chunk, k = (k + 1) % NPIPE) {
 		size_t nb = n_blocks - done < chunk ? n_blocks - done : chunk;
@@ -540,9 +543,10 @@ int csnappy_batch_decompress_host(const void *h_in, uint64_t in_stride, const ui
 		a.status = d_st;
 		a.flags = flags;
 		a.lanes = g_decompress_lanes;
-	a.stage_input = g_stage_input;
-	a.smem_kb = g_smem_kb;
+		a.stage_input = g_stage_input;
+		a.smem_kb = g_smem_kb;
 		a.ctas_per_sm = g_ctas_per_sm;
+		a.counter = (uint32_t *)C.d_ctr2[k].p;
 		TRY("decompress launch", csb_launch_decompress(&a, (csb_stream_t)s));
 		TRY("D2H data", cudaMemcpyAsync((uint8_t *)h_out + done * out_stride, C.d_out2[k].p, nb * out_stride,
 						cudaMemcpyDeviceToHost, s));
@@ -808,8 +812,8 @@ int csnappy_bc_decompress_host(const void *h_container, uint64_t container_lengt
 				a.max_in_len = longest;
 				a.counter = (uint32_t *)b->d_ctr.p;
 				a.lanes = g_decompress_lanes;
-	a.stage_input = g_stage_input;
-	a.smem_kb = g_smem_kb;
+				a.stage_input = g_stage_input;
+				a.smem_kb = g_smem_kb;
 				a.ctas_per_sm = g_ctas_per_sm;
 				TRY("decompress launch", csb_launch_decompress(&a, (csb_stream_t)b->s));
 				TRY("D2H pages", cudaMemcpyAsync((uint8_t *)h_out + done * page_size, b->d_out.p, (size_t)nb * page_size,
