@@ -358,7 +358,7 @@ def main():
         }
         if e2e_max:
             line["e2e"] = {"value": round(2 * total_n / (e2e_max * 1e-3) / 1e9, 2), "unit": "GB/s",
-                           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                           "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
                            "ms_per_step": round(e2e_max, 2),
                            "api": "csnappy_bc_compress_host + csnappy_bc_decompress_host (block_compressor page container), pinned host buffers"}
         if world == 1 and not args.no_cpu:
