@@ -4,8 +4,11 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--pages P]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1], "zram-style batch"): per GPU 1 Mi synthetic 4 KiB pages
-(50 % word text, 25 % zero, 25 % random; csnappy_b200/synth.py), csnappy_compress_fragment
+Workload (BASELINE.json configs[1], "zram-style batch", as defined in SURVEY.md 8d config 2): per GPU
+1 Mi synthetic 4 KiB pages, class per page from splitmix64(seed ^ index): 50 % text (a 4096-byte slice
+of the reference's urls.10K corpus at a seeded offset; --text words switches to the purely synthetic
+Zipf word stream, which is also reported as `alt_workload`), 25 % zero, 25 % random
+(csnappy_b200/synth.py), csnappy_compress_fragment
 semantics with workmem_bytes_power_of_two = 13, then csnappy_decompress_noheader of the result.
 One STEP = compress the whole batch + decompress the whole batch.  Metric: GB/s of UNCOMPRESSED
 bytes through the codec = (bytes compressed + bytes decompressed) / step time, whole job
@@ -40,6 +43,8 @@ PAGE = 4096
 WM = 13
 SEED = 0x5EED0001
 METRIC = "compress+decompress throughput, GB/s of uncompressed data, 4 KiB pages (wm 13)"
+TEXT_DESC = {"urls": "4096-byte slices of the reference's urls.10K at seeded offsets",
+             "words": "Zipf(1.1) word stream over a 4096-word vocabulary"}
 
 
 def host_cores() -> int:
@@ -140,7 +145,7 @@ def run_reference(args, rank: int, world: int):
     cores = host_cores()
     S = min(args.pages, 1 << 16)  # bounded sample per step: 64 Ki pages = 256 MiB
     dev = "cuda" if torch.cuda.is_available() else "cpu"
-    pages = synth.mixed_pages(S, PAGE, seed=SEED, device=dev).view(S, PAGE).cpu().numpy()
+    pages = synth.mixed_pages(S, PAGE, seed=SEED, device=dev, text=args.text).view(S, PAGE).cpu().numpy()
     times = []
     for it in range(args.warmup + args.steps):
         tc, td, _, _ = cpu_codec_pass(pages, cores, impl, repeats=1)
@@ -152,8 +157,9 @@ def run_reference(args, rank: int, world: int):
         "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": "GB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * total / args.steps, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "zram-style batch: synthetic 4 KiB pages (50% text / 25% zero / 25% random), wm 13, "
-                               "compress then decompress", "pages_per_gpu": args.pages, "page_bytes": PAGE, "wm": WM},
+        "config": {"workload": f"zram-style batch: synthetic 4 KiB pages (50% text [{TEXT_DESC[args.text]}] / 25% zero / "
+                               "25% random), wm 13, compress then decompress", "pages_per_gpu": args.pages,
+                   "page_bytes": PAGE, "wm": WM},
         "cpu_baseline": {"value": round(value, 3), "unit": "GB/s", "cores": cores, "kind": impl,
                          "sample": f"{S} pages ({S * PAGE >> 20} MiB) per step, compress + decompress, "
                                    f"{cores} pthreads, static partition"},
@@ -177,6 +183,10 @@ def main():
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--stage-d", type=int, default=0)
     ap.add_argument("--smem-d", type=int, default=0)
+    ap.add_argument("--text", default="urls", choices=["urls", "words"],
+                    help="text class (SURVEY.md 8d config 2): 4 KiB slices of the reference's urls.10K at seeded "
+                         "offsets (default), or the purely synthetic alternative, a Zipf(1.1) word stream")
+    ap.add_argument("--no-alt", action="store_true", help="skip the short run on the alternative text class")
     ap.add_argument("--only", default="", choices=["", "text", "zero", "random"],
                     help="diagnostic: make every page of one class (not the BASELINE workload)")
     args = ap.parse_args()
@@ -216,7 +226,7 @@ def main():
 
     B = args.pages
     first, _ = shard.block_range(B * world, rank, world)  # weak scaling: rank r owns pages [r*B, (r+1)*B)
-    pages = synth.mixed_pages(B, PAGE, seed=SEED, device=dev, first_page=first, only=args.only)
+    pages = synth.mixed_pages(B, PAGE, seed=SEED, device=dev, first_page=first, only=args.only, text=args.text)
     ostride = cs.api.out_stride_for(PAGE)
     comp = torch.empty(B * ostride, dtype=torch.uint8, device=dev)
     comp_len = torch.empty(B, dtype=torch.int32, device=dev)
@@ -305,6 +315,47 @@ def main():
         d2h = payload + 4 * B + 8 * ((B + 8191) // 8192) + B * PAGE + 8 * B
         del h_in, h_cont, h_back
 
+    # ---- the alternative text class, short run (device-resident only) ---------------------
+    alt = None
+    if not args.no_alt and not args.only:
+        other = "words" if args.text == "urls" else "urls"
+        Ba = min(B, 1 << 18)
+        pa = synth.mixed_pages(Ba, PAGE, seed=SEED, device=dev, first_page=first, text=other)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        a_comp = torch.empty(Ba * ostride, dtype=torch.uint8, device=dev)
+        a_len = torch.empty(Ba, dtype=torch.int32, device=dev)
+        a_back = torch.empty(Ba * PAGE, dtype=torch.uint8, device=dev)
+        a_blen = torch.empty(Ba, dtype=torch.int32, device=dev)
+        a_st = torch.empty(Ba, dtype=torch.int32, device=dev)
+
+        def alt_step(record):
+            if record:
+                ev[0].record()
+            cs.batch_compress_fragments(pa, PAGE, Ba, WM, out=a_comp, out_len=a_len, out_stride=ostride)
+            if record:
+                ev[1].record()
+            cs.batch_decompress(a_comp, a_len, Ba, PAGE, in_stride=ostride, out=a_back, out_stride=PAGE,
+                                out_len=a_blen, status=a_st)
+            if record:
+                ev[2].record()
+
+        for _ in range(3):
+            alt_step(False)
+        tca, tda = [], []
+        for _ in range(3):
+            alt_step(True)
+            torch.cuda.synchronize()
+            tca.append(ev[0].elapsed_time(ev[1]))
+            tda.append(ev[1].elapsed_time(ev[2]))
+        assert int((a_st != 0).sum()) == 0 and torch.equal(a_back, pa)
+        alt = {"text": TEXT_DESC[other], "pages_per_gpu": Ba,
+               "ratio": round(float(a_len.sum()) / (Ba * PAGE), 4),
+               "compress_gbs": round(world * Ba * PAGE / (statistics.mean(tca) * 1e-3) / 1e9, 2),
+               "decompress_gbs": round(world * Ba * PAGE / (statistics.mean(tda) * 1e-3) / 1e9, 2),
+               "value": round(2 * world * Ba * PAGE / ((statistics.mean(tca) + statistics.mean(tda)) * 1e-3) / 1e9, 2),
+               "note": "rank 0's times, mean of 3 steps after 3 warm-ups"}
+        del pa, a_comp, a_back
+
     # ---- reduce over ranks: max time, sum bytes -------------------------------------------
     vals = torch.tensor([elapsed_ms, tc_ms, td_ms, e2e_ms or 0.0], dtype=torch.float64, device=dev)
     sums = torch.tensor([float(B * PAGE), float(csum), float(launches)], dtype=torch.float64, device=dev)
@@ -333,8 +384,8 @@ def main():
             "metric": METRIC, "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "zram-style batch: synthetic 4 KiB pages (50% text / 25% zero / 25% random), "
-                                   "wm 13, compress then decompress", "pages_per_gpu": B, "page_bytes": PAGE,
+            "config": {"workload": f"zram-style batch: synthetic 4 KiB pages (50% text [{TEXT_DESC[args.text]}] / 25% zero / "
+                                   "25% random), wm 13, compress then decompress", "pages_per_gpu": B, "page_bytes": PAGE,
                        "wm": WM, "ratio": round(total_c / total_n, 4), "parallelism": f"shard{world} (no collective)",
                        "l2": "inputs (4 GiB per GPU) exceed the 126 MB L2; no explicit flush",
                        "value_definition": "(bytes compressed + bytes decompressed) / step time"},
@@ -356,6 +407,8 @@ def main():
             "gpu_launches": int(total_launches),
             "clocks": clocks,
         }
+        if alt:
+            line["alt_workload"] = alt
         if e2e_max:
             line["e2e"] = {"value": round(2 * total_n / (e2e_max * 1e-3) / 1e9, 2), "unit": "GB/s",
                            "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,

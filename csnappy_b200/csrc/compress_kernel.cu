@@ -523,13 +523,10 @@ extern "C" int csb_launch_compress(const struct csb_compress_args *a, csb_stream
 	const int threads = (groups * G + 31) / 32 * 32;  // whole warps; surplus lanes exit at once
 	const size_t smem = (size_t)groups * p.group_smem;
 
-	uint32_t *counter = a->counter;
-	cudaError_t ce = cudaSuccess;
+	uint32_t *counter = a->counter ? a->counter : next_counter();
 	if (!counter)
-		ce = cudaMallocAsync((void **)&counter, sizeof(uint32_t), s);
-	if (ce != cudaSuccess)
-		return (int)ce;
-	ce = cudaMemsetAsync(counter, 0, sizeof(uint32_t), s);
+		return (int)cudaErrorMemoryAllocation;
+	cudaError_t ce = cudaMemsetAsync(counter, 0, sizeof(uint32_t), s);
 	if (ce != cudaSuccess)
 		return (int)ce;
 	p.counter = counter;
@@ -539,7 +536,5 @@ extern "C" int csb_launch_compress(const struct csb_compress_args *a, csb_stream
 	case 8: e = launch_compress_g<8>(p, threads, (int)ctas, smem, s); break;
 	default: e = (int)cudaErrorInvalidValue; break;
 	}
-	if (!a->counter)
-		cudaFreeAsync(counter, s);
 	return e;
 }

@@ -215,5 +215,6 @@ struct DeviceInfo {
 // cached per-device query; returns a cudaError_t
 int device_info(DeviceInfo *out);
 void count_launch();
+uint32_t *next_counter();  // a device word for a kernel's block-claim counter (nullptr on failure)
 
 }  // namespace csb

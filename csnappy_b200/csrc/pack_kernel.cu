@@ -41,6 +41,30 @@ int device_info(DeviceInfo *out)
 	return 0;
 }
 
+// Block-claim counters: a per-device ring of device words handed out round-robin, so a launch never
+// allocates (a stream-ordered allocation per launch showed up as milliseconds of launch jitter).
+// A slot is reused after kCounterSlots further launches on this device -- far more than can be in flight.
+constexpr unsigned kCounterSlots = 4096;
+uint32_t *next_counter()
+{
+	static std::mutex mu;
+	static uint32_t *ring[64];
+	static std::atomic<unsigned> cursor[64];
+	int dev = 0;
+	if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64)
+		return nullptr;
+	if (!ring[dev]) {
+		std::lock_guard<std::mutex> lk(mu);
+		if (!ring[dev]) {
+			uint32_t *p = nullptr;
+			if (cudaMalloc((void **)&p, kCounterSlots * sizeof(uint32_t)) != cudaSuccess)
+				return nullptr;
+			ring[dev] = p;
+		}
+	}
+	return ring[dev] + (cursor[dev].fetch_add(1, std::memory_order_relaxed) % kCounterSlots);
+}
+
 constexpr int kScanThreads = 1024;
 
 // Stored-block rule of block_compressor.c:316-318: a block whose compressed size is not smaller than

@@ -2,14 +2,15 @@
 
 zram-style batch: pages of `page_len` bytes, class per page from
 splitmix64(seed ^ page_index): 50 % text, 25 % zero, 25 % random.
-  text    a page_len slice of a Zipf(1.1) word stream over a 4096-word lowercase
-          vocabulary (space / newline separated), at offset h mod (pool - page_len)
+  text    text="urls": a page_len slice of the reference's urls.10K corpus (committed copy:
+          tests/golden/urls.10K.gz) at offset h mod (702087 - page_len) -- the primary definition
+          of SURVEY.md 8d config 2;  text="words": the purely synthetic alternative, a page_len
+          slice of a Zipf(1.1) word stream over a 4096-word lowercase vocabulary
   zero    all zero bytes
   random  uniform bytes
-There is no network and no /root/reference on the GPU box, so the text class is
-purely synthetic (the urls.10K-slice variant of SURVEY.md 8d is used only by the
-tests, from the committed fixture).  Generation uses torch only as device-memory
-plumbing (gather / randint); it is not part of the measured path.
+Nothing reads /root/reference: the urls corpus comes from the committed fixture.
+Generation uses torch only as device-memory plumbing (gather / randint); it is not
+part of the measured path.
 """
 from __future__ import annotations
 
@@ -49,6 +50,17 @@ def text_pool(nbytes: int, seed: int = 0x5EED0002) -> np.ndarray:
     return out[:nbytes]
 
 
+def urls_pool() -> np.ndarray:
+    """The reference's own text corpus (testdata/urls.10K, committed as tests/golden/urls.10K.gz): the
+    primary text class of SURVEY.md 8d config 2 is a 4096-byte slice of it at a seeded offset."""
+    import gzip
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "urls.10K.gz")
+    with gzip.open(path, "rb") as f:
+        return np.frombuffer(f.read(), dtype=np.uint8).copy()
+
+
 def page_classes(n_pages: int, seed: int, first_page: int = 0):
     """-> (cls uint8 [n]: 0 text, 1 zero, 2 random ; h uint64 [n])."""
     with np.errstate(over="ignore"):
@@ -60,7 +72,7 @@ def page_classes(n_pages: int, seed: int, first_page: int = 0):
 
 
 def mixed_pages(n_pages: int, page_len: int = 4096, seed: int = 0x5EED0001, device="cuda", first_page: int = 0,
-                pool_bytes: int = 8 << 20, text_only: bool = False, only: str = ""):
+                pool_bytes: int = 8 << 20, text_only: bool = False, only: str = "", text: str = "words"):
     """uint8 tensor [n_pages * page_len] on `device` holding the zram-style mixed batch.
     `first_page` lets each rank of a sharded run generate exactly its slice of the global batch."""
     import torch
@@ -70,7 +82,12 @@ def mixed_pages(n_pages: int, page_len: int = 4096, seed: int = 0x5EED0001, devi
         cls[:] = 0
     elif only:
         cls[:] = {"zero": 1, "random": 2}[only]
-    pool = torch.from_numpy(text_pool(pool_bytes)).to(device)
+    if text == "urls":
+        host_pool = urls_pool()
+        pool_bytes = len(host_pool)
+    else:
+        host_pool = text_pool(pool_bytes)
+    pool = torch.from_numpy(host_pool).to(device)
     windows = pool.unfold(0, page_len, 1)  # [pool - page_len + 1, page_len] overlapping view
     pages = torch.zeros((n_pages, page_len), dtype=torch.uint8, device=device)
     text_idx = np.nonzero(cls == 0)[0]

@@ -18,13 +18,14 @@ ap.add_argument("--lanes-d", default="32")
 ap.add_argument("--ctas", default="0")
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--only", default="")
+ap.add_argument("--text", default="words")
 ap.add_argument("--stage-d", default="0")
 ap.add_argument("--smem-d", default="0")
 args = ap.parse_args()
 for lc, ld, ct, sd, kb in itertools.product(args.lanes_c.split(","), args.lanes_d.split(","), args.ctas.split(","),
                                          args.stage_d.split(","), args.smem_d.split(",")):
     cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--pages", str(args.pages), "--steps", str(args.steps),
-           "--warmup", "3", "--no-e2e", "--no-cpu", "--lanes-c", lc, "--lanes-d", ld, "--ctas-per-sm", ct, "--stage-d", sd, "--smem-d", kb] + (["--only", args.only] if args.only else [])
+           "--warmup", "3", "--no-e2e", "--no-cpu", "--lanes-c", lc, "--lanes-d", ld, "--ctas-per-sm", ct, "--stage-d", sd, "--smem-d", kb] + (["--only", args.only] if args.only else []) + ["--text", args.text]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     try:
         d = json.loads(r.stdout.strip().splitlines()[-1])
