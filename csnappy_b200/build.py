@@ -31,6 +31,7 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v", "--expt-relaxed-constexpr",
 ]
+NVCC_FLAGS += os.environ.get("CSB_NVCC_EXTRA", "").split()  # experiments: e.g. -DCSB_CUT_MIN=20
 CC_FLAGS = ["-O2", "-std=gnu11", "-Wall", "-Wextra", "-fPIC", "-I" + os.path.join(CUDA_HOME, "include")]
 
 
