@@ -40,6 +40,7 @@ struct CompressParams {
 	csb_compress_args a;
 	uint32_t *counter;     // dynamic block claim
 	uint32_t table_bytes;  // 1 << wm
+	uint32_t in_cap;       // longest block the staging area holds (<= 32768)
 	uint32_t in_area;      // bytes reserved for the staged input incl. pad (multiple of 16)
 	uint32_t group_smem;   // table_bytes + in_area + 16 (mbarrier) + 8 * kTokens
 	uint32_t groups;       // groups per CTA that own shared memory
@@ -252,8 +253,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 				if (left < n)
 					n = (uint32_t)left;
 			}
-			if (n > CSB_FRAGMENT_MAX)
-				n = CSB_FRAGMENT_MAX;  // REQUIRES of the reference (csnappy.h:38)
+			if (n > p.in_cap)
+				n = p.in_cap;  // REQUIRES of the reference (csnappy.h:38): at most 32768, and never more than was staged for
 			const uint8_t *src = a.in + in_at;
 			dst = a.out + (uint64_t)blk * a.out_stride;
 			// table size for this block (csnappy_compress.c:638-646 when SHRINK_TABLE is set)
@@ -494,6 +495,7 @@ extern "C" int csb_launch_compress(const struct csb_compress_args *a, csb_stream
 		in_cap = (!a->in_off && a->in_stride && a->in_stride < CSB_FRAGMENT_MAX) ? (uint32_t)a->in_stride : CSB_FRAGMENT_MAX;
 	if (in_cap > CSB_FRAGMENT_MAX)
 		in_cap = CSB_FRAGMENT_MAX;
+	p.in_cap = in_cap;
 	p.in_area = ((in_cap + 15u) & ~15u) + kInPad;
 	p.group_smem = p.table_bytes + p.in_area + 16 + 8 * kTokens;
 

@@ -418,3 +418,49 @@ def test_scale_mixed_pages_roundtrip_and_oracle_sample(cs, chk):
     got = out.view(B, ostride)[:S].cpu().numpy()
     mask = np.arange(ostride)[None, :] < ref_len[:, None]
     assert (got[mask] == ref_out[:, :ostride][mask]).all()
+
+
+def test_config3_text_fragments_32k_scale(cs, chk):
+    """BASELINE config 3 shape: 32 KiB text-like fragments (wm 15 and 16), here 2048 of them (64 MiB):
+    exact round trip on the device, byte identity with the reference on a sample, and the packed
+    stream (size index + payload, block_compressor style) decodes again from arbitrary alignment."""
+    from csnappy_b200 import synth
+
+    n, L = 2048, 32768
+    d = synth.text_fragments(n, L, device="cuda", pool_bytes=4 << 20)
+    ostride = cs.api.out_stride_for(L)
+    for wm in (15, 16):
+        out, out_len = cs.batch_compress_fragments(d, L, n, wm)
+        back, back_len, status = cs.batch_decompress(out, out_len, n, L, in_stride=ostride)
+        torch.cuda.synchronize()
+        assert int((status != 0).sum()) == 0 and int((back_len != L).sum()) == 0 and torch.equal(back, d)
+        host = d.view(n, L)[::97].cpu().numpy()
+        o = out.view(n, ostride)[::97].cpu().numpy()
+        ol = out_len[::97].cpu().numpy()
+        for i in range(host.shape[0]):
+            assert o[i, : ol[i]].tobytes() == chk.compress_fragment(host[i].tobytes(), wm), (wm, i)
+    packed, off = cs.batch_pack(out, ostride, out_len, n)
+    back2, back_len2, st2 = cs.batch_decompress(packed, out_len, n, L, in_off=off[:-1].contiguous())
+    torch.cuda.synchronize()
+    assert int(off[-1]) == int(out_len.sum()) and int((st2 != 0).sum()) == 0 and torch.equal(back2, d)
+
+
+def test_config4_decode_only_of_a_packed_corpus(cs, chk):
+    """BASELINE config 4 shape: decode-only of a corpus pre-compressed BY THE REFERENCE in 4 KiB units with a
+    u32 size index, payloads packed back to back (arbitrary alignment) -- checksum-of-everything style
+    properties: every status 0, every length 4096, output == corpus."""
+    from csnappy_b200 import synth
+
+    n, L = 1 << 15, 4096
+    corpus = synth.mixed_pages(n, L, seed=0x5EED0003, device="cpu", pool_bytes=1 << 20, text="urls").numpy().reshape(n, L)
+    ref_out, ref_len, _ = oracle.batch_compress(corpus, 13, chk.kind, threads=8)
+    offs = np.concatenate([[0], np.cumsum(ref_len.astype(np.int64))])
+    packed = np.zeros(int(offs[-1]) + 16, dtype=np.uint8)
+    mask = np.arange(ref_out.shape[1])[None, :] < ref_len[:, None]
+    packed[: int(offs[-1])] = ref_out[mask]
+    out, out_len, status = cs.batch_decompress(torch.from_numpy(packed).cuda(),
+                                               torch.from_numpy(ref_len.astype(np.int32)).cuda(), n, L,
+                                               in_off=torch.from_numpy(offs[:-1].copy()).cuda(), out_stride=L)
+    torch.cuda.synchronize()
+    assert int((status != 0).sum()) == 0 and int((out_len != L).sum()) == 0
+    assert (out.cpu().numpy().reshape(n, L) == corpus).all()
