@@ -23,8 +23,10 @@
 //                         copies G bytes per step, overlapping copies (offset < length) as a
 //                         pattern fill or in offset-sized rounds, all against shared memory.
 //              The finished block leaves with one bulk async store (shared -> global).
-//   streaming  anything larger (whole multi-chunk streams through the drop-in API): input and
-//              output stay in global memory, one tag at a time, back-references read through L2.
+//   global     blocks that do not fit shared memory (whole multi-chunk streams through the drop-in API), or
+//              of which fewer than 8 would fit per SM (32 KiB fragments): same three phases, but the input is
+//              read through L1 and the output lives in global memory, back-references through L2; no staging
+//              area, so every warp of the CTA runs its own block and the L2 latency is hidden by their number.
 #include "device_common.cuh"
 #include "kernels.h"
 
@@ -32,6 +34,7 @@ namespace csb {
 
 constexpr int E_OK = 0, E_HEADER_BAD = -1, E_OUTPUT_INSUF = -2, E_OUTPUT_OVERRUN = -3, E_DATA_MALFORMED = -5;
 constexpr int kMaxThreadsD = 832;
+constexpr int kMinStagedGroups = 8;  // fewer staged blocks per SM than this: use the global path instead
 
 
 struct DecompressParams {
@@ -43,28 +46,164 @@ struct DecompressParams {
 	uint32_t groups;  // groups per CTA that own shared memory
 };
 
-// ---- streaming path: one tag at a time against global memory ---------------------------------
+// ---- global path: blocks that do not fit shared memory -----------------------------------------
+// Same three phases as the staged path (walk / lane-per-tag decode / steps of G/8 tags), but the
+// compressed block is read through L1 (ld.global.nc) and the output lives in global memory:
+// back-references are read through L2 (ld.global.cg) after the __syncwarp that follows every step, which
+// orders them behind the stores of earlier steps.  Needs no staging area, so a CTA runs as many groups
+// as it has warps; the latency of L2 is hidden by the number of groups, not inside one.
+// Batches are G/2 tags so that the G walk words + 8-byte descriptors of the staged layout (12 G bytes)
+// hold 2 walk words + a 16-byte descriptor per tag.
 template <int G>
-__device__ __forceinline__ int decode_streaming(const Group<G> &g, const uint8_t *ib, uint32_t ilen, uint8_t *ob,
-						uint32_t cap, uint32_t *produced_out)
+__device__ __forceinline__ int decode_global(const Group<G> &g, const uint8_t *src, uint32_t ilen, uint8_t *dst,
+					     uint32_t cap, uint32_t lut_a, uint32_t meta_a, uint32_t *produced_out)
 {
+	constexpr uint32_t GB = G / 2, Q = G / 8;
+	const uint32_t pos_a = meta_a, out_a = meta_a + 4 * GB, desc_a = meta_a + 8 * GB;
+	const uint32_t sub = g.lane & 7u, tq = g.lane >> 3;
 	uint32_t pos = 0, produced = 0;
-	while (pos < ilen) {
-		const uint32_t tag = ib[pos++];
-		const uint32_t kind = tag & 3u;
-		uint32_t len;
-		if (kind == 0) {
-			len = (tag >> 2) + 1;
-			if (len > 60) {
-				const uint32_t nb = len - 60;
-				if (ilen - pos < nb)
-					return E_DATA_MALFORMED;
-				uint32_t v = 0;
-				for (uint32_t b = 0; b < nb; ++b)
-					v |= (uint32_t)ib[pos + b] << (8 * b);
-				pos += nb;
-				len = v + 1;  // 0xffffffff wraps to a zero-length literal (csnappy_decompress.c:370)
+	for (;;) {
+		// ---- walk ----
+		uint32_t k = 0, e = 0;
+		for (; k < GB; ++k) {
+			if (pos >= ilen)
+				break;
+			e = lds_u32(lut_a + 4 * (uint32_t)__ldg(src + pos));
+			sts_u32(pos_a + 4 * k, pos);
+			sts_u32(out_a + 4 * k, produced);
+			const uint32_t adv = e & 0xffffu, len = e >> 16;
+			if (adv == 0xffffu || ilen - pos < adv || cap - produced < len)
+				break;
+			pos += adv;
+			produced += len;
+		}
+		const uint32_t ntags = k;
+		int werr = E_OK;
+		bool stop = false, longlit = false;
+		if (k < GB) {
+			if (pos >= ilen)
+				stop = true;  // end of input at a tag boundary
+			else if ((e & 0xffffu) == 0xffffu)
+				longlit = true;
+			else if (ilen - pos < (e & 0xffffu))
+				werr = E_DATA_MALFORMED;  // literal payload or copy offset bytes cut off by end of input
+			else
+				werr = E_OUTPUT_OVERRUN;  // (a copy still has its offset validated first)
+		}
+		g.sync();
+
+		// ---- decode: lane k owns tag k ----
+		// descriptor: x = source (output offset, or input position for a literal), y = destination output offset,
+		//             z = len | literal << 8 | overlap << 9 | serial step << 10 | period << 16 | rounds << 24
+		uint32_t dx = 0, dy = 0, dz = 0, mylen = 0, myo = 0, src_end = 0;
+		bool bad = false, dep = false, cp = false;
+		if (g.lane < ntags + (werr == E_OUTPUT_OVERRUN ? 1u : 0u)) {
+			const uint32_t p = lds_u32(pos_a + 4 * g.lane), o = lds_u32(out_a + 4 * g.lane);
+			const uint32_t tag = __ldg(src + p);
+			const uint32_t kind = tag & 3u;
+			uint32_t len = (tag >> 2) + 1;
+			dy = o;
+			if (kind == 0) {
+				dx = p + 1;
+				dz = len | (1u << 8);
+			} else {
+				uint32_t off = __ldg(src + p + 1);
+				if (kind == 1) {
+					len = ((tag >> 2) & 7u) + 4;
+					off |= (tag >> 5) << 8;
+				} else {
+					off |= (uint32_t)__ldg(src + p + 2) << 8;
+					if (kind == 3)
+						off |= ((uint32_t)__ldg(src + p + 3) << 16) | ((uint32_t)__ldg(src + p + 4) << 24);
+				}
+				bad = off - 1u >= o;  // off == 0 or off > produced, csnappy_decompress.c:302
+				dx = o - off;
+				dz = len;
+				cp = true;
+				src_end = o - off + len;
+				if (off < len) {
+					dz |= (1u << 9) | (off << 16);
+					dep = true;
+				}
 			}
+			mylen = g.lane < ntags ? len : 0u;
+			myo = o;
+		}
+		const unsigned badmask = g.ballot(bad);
+		if (badmask || werr != E_OK)
+			return badmask ? E_DATA_MALFORMED : werr;  // an invalid offset at or before the failing tag wins
+		{
+			const uint32_t first = g.lane & ~(Q - 1);
+			const uint32_t o_first = g.bcast(myo, (int)first);
+			dep = dep || (cp && g.lane < ntags && src_end > o_first);
+			const unsigned dm = g.ballot(dep);
+			uint32_t smax = mylen;
+#pragma unroll
+			for (uint32_t x = 1; x < Q; x <<= 1)
+				smax = max(smax, __shfl_xor_sync(g.mask, smax, x, G));
+			if (Q == 1 || ((dm >> first) & ((1u << Q) - 1u)))
+				dz |= 1u << 10;
+			dz |= ((smax + 7) >> 3) << 24;
+		}
+		if (g.lane < GB)
+			sts_v4(desc_a + 16 * g.lane, dx, dy, dz, 0);
+		g.sync();
+
+		// ---- execute in stream order ----
+		for (uint32_t t = 0; t < ntags; t += Q) {
+			const uint4 d = lds_v4(desc_a + 16 * min(t + tq, GB - 1));
+			if (!(d.z & (1u << 10))) {
+				// independent step: 8 lanes per tag, all Q tags at once
+				const uint32_t len = t + tq < ntags ? (d.z & 0xffu) : 0u, rounds = (d.z >> 24) & 0xfu;
+				for (uint32_t j = 0; j < rounds; ++j) {
+					const uint32_t i = sub + 8 * j;
+					if (i < len)
+						dst[d.y + i] = (d.z & (1u << 8)) ? __ldg(src + d.x + i) : __ldcg(dst + d.x + i);
+				}
+				g.sync();
+				continue;
+			}
+			const uint32_t t_end = min(t + Q, ntags);
+			for (uint32_t u = t; u < t_end; ++u) {
+				const uint4 c = lds_v4(desc_a + 16 * u);
+				const uint32_t len = c.z & 0xffu;
+				uint8_t *to = dst + c.y;
+				if (c.z & (1u << 8)) {
+					for (uint32_t i = g.lane; i < len; i += G)
+						to[i] = __ldg(src + c.x + i);
+				} else {
+					const uint8_t *from = dst + c.x;
+					const uint32_t off = (c.z >> 16) & 0xffu;
+					if (!(c.z & (1u << 9))) {
+						for (uint32_t i = g.lane; i < len; i += G)
+							to[i] = __ldcg(from + i);
+					} else if (off >= (uint32_t)G) {
+						for (uint32_t q = 0; q < len; q += G) {
+							const uint32_t i = q + g.lane;
+							if (i < len)
+								to[i] = __ldcg(from + i);
+							g.sync();
+						}
+					} else {
+						for (uint32_t i = g.lane; i < len; i += G)
+							to[i] = __ldcg(from + (i % off));
+					}
+				}
+				g.sync();
+			}
+		}
+
+		// ---- a long literal ends the batch and is copied by all lanes ----
+		if (longlit) {
+			const uint32_t tag = __ldg(src + pos++);
+			const uint32_t nb = (tag >> 2) + 1 - 60;
+			if (ilen - pos < nb)
+				return E_DATA_MALFORMED;
+			uint32_t v = 0;
+			for (uint32_t b = 0; b < nb; ++b)
+				v |= (uint32_t)__ldg(src + pos + b) << (8 * b);
+			pos += nb;
+			const uint32_t len = v + 1;  // 0xffffffff wraps to a zero-length literal (csnappy_decompress.c:370)
 			if ((int32_t)len >= 0) {
 				if (ilen - pos < len)
 					return E_DATA_MALFORMED;
@@ -73,48 +212,23 @@ __device__ __forceinline__ int decode_streaming(const Group<G> &g, const uint8_t
 			}
 			if (cap - produced < len)
 				return E_OUTPUT_OVERRUN;
-			for (uint32_t i = g.lane; i < len; i += G)
-				ob[produced + i] = ib[pos + i];
+			uint32_t i = g.lane;
+			for (; i + 3 * G < len; i += 4 * G) {
+				const uint8_t b0 = __ldg(src + pos + i), b1 = __ldg(src + pos + i + G), b2 = __ldg(src + pos + i + 2 * G),
+					      b3 = __ldg(src + pos + i + 3 * G);
+				dst[produced + i] = b0;
+				dst[produced + i + G] = b1;
+				dst[produced + i + 2 * G] = b2;
+				dst[produced + i + 3 * G] = b3;
+			}
+			for (; i < len; i += G)
+				dst[produced + i] = __ldg(src + pos + i);
 			pos += len;
-		} else {
-			const uint32_t nb = kind == 3 ? 4u : kind;
-			if (ilen - pos < nb)
-				return E_DATA_MALFORMED;
-			uint32_t off = ib[pos];
-			if (nb >= 2)
-				off |= (uint32_t)ib[pos + 1] << 8;
-			if (nb == 4)
-				off |= ((uint32_t)ib[pos + 2] << 16) | ((uint32_t)ib[pos + 3] << 24);
-			pos += nb;
-			if (kind == 1) {
-				len = ((tag >> 2) & 7u) + 4;
-				off |= (tag >> 5) << 8;
-			} else {
-				len = (tag >> 2) + 1;
-			}
-			if (off - 1u >= produced)  // off == 0 or off > produced, csnappy_decompress.c:302
-				return E_DATA_MALFORMED;
-			if (cap - produced < len)
-				return E_OUTPUT_OVERRUN;
-			const uint8_t *from = ob + produced - off;
-			// written by other lanes of this group: read through L2
-			if (off >= len) {
-				for (uint32_t i = g.lane; i < len; i += G)
-					ob[produced + i] = __ldcg(from + i);
-			} else if (off >= (uint32_t)G) {
-				for (uint32_t c = 0; c < len; c += G) {
-					const uint32_t i = c + g.lane;
-					if (i < len)
-						ob[produced + i] = __ldcg(from + i);
-					g.sync();
-				}
-			} else {
-				for (uint32_t i = g.lane; i < len; i += G)
-					ob[produced + i] = __ldcg(from + (i % off));
-			}
+			produced += len;
+			g.sync();
 		}
-		produced += len;
-		g.sync();
+		if (stop)
+			break;
 	}
 	*produced_out = produced;
 	return E_OK;
@@ -468,7 +582,7 @@ __global__ void __launch_bounds__(kMaxThreadsD, 1) decompress_kernel(const Decom
 						dst[i] = src[i];
 					produced = ilen;
 				} else {
-					rc = decode_streaming<G>(g, src, ilen, dst, cap, &produced);
+					rc = decode_global<G>(g, src, ilen, dst, cap, lut_a, meta_a, &produced);
 				}
 				if (g.lane == 0) {
 					a.status[blk] = rc;
@@ -622,11 +736,11 @@ extern "C" int csb_launch_decompress(const struct csb_decompress_args *a, csb_st
 	const int max_groups = kMaxThreadsD / G;
 	if (groups > max_groups)
 		groups = max_groups;
-	if (groups < 1) {
-		// cannot stage even one block: run streaming only
+	if ((groups < kMinStagedGroups && a->stage_input != 1) || a->stage_input == 3) {
+		// too few blocks fit shared memory for their chains to hide each other: global path, one group per warp slot
 		p.in_area = p.out_area = 0;
 		p.group_smem = meta_bytes;
-		groups = 256 / G;
+		groups = kMaxThreadsD / G;
 	}
 	long want = ((long)a->n_blocks + groups - 1) / groups;
 	long ctas = (long)di.sm_count * ctas_per_sm;

@@ -166,6 +166,16 @@ __device__ __forceinline__ uint2 lds_v2(uint32_t a)
 	asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
 	return v;
 }
+__device__ __forceinline__ uint4 lds_v4(uint32_t a)
+{
+	uint4 v;
+	asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+	return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w)
+{
+	asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
 __device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v)
 {
 	asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");

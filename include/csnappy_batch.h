@@ -136,8 +136,8 @@ int csnappy_b200_device_ok(void);	   /* 1 if a CUDA device is usable */
 const char *csnappy_b200_last_error(void); /* text of the last device error (thread local) */
 uint64_t csnappy_b200_kernel_launches(void); /* kernels launched by this library so far */
 /* key: "compress_lanes" | "decompress_lanes" (lanes cooperating on one block: 8/16/32),
- *      "ctas_per_sm", "decompress_stage_input" (2: read compressed blocks through L1 instead of
- *      staging them in shared memory), "decompress_smem_kb" (shared memory per SM in unstaged mode);
+ *      "ctas_per_sm", "decompress_stage_input" (1: always stage blocks in shared memory, 2: stage only
+ *      the output and read compressed blocks through L1, 3: never stage -- decode against global memory), "decompress_smem_kb" (shared memory per SM in unstaged mode);
  *      value 0 restores the default.  Returns 0 or CSNAPPY_E_BAD_ARG. */
 int csnappy_b200_set_tuning(const char *key, int value);
 
