@@ -347,8 +347,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 					if (valid && q != pp)
 						same |= 1u << (q - wbase);
 				}
-				g.sync();
 			}
+			g.sync();  // every lane has read back before anybody restores
 			if (valid)
 				sts_u16(slot, old);  // back to the state before this window
 			if (!paired)

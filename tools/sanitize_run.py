@@ -36,4 +36,19 @@ o, ol = cs.batch_compress_fragments(frag, 32768, 6, 15)
 b, bl, st = cs.batch_decompress(o, ol, 6, 32768, in_stride=cs.api.out_stride_for(32768))
 torch.cuda.synchronize()
 assert int((st != 0).sum()) == 0 and torch.equal(b.view(6, 32768), frag.view(6, 32768))
+# whole multi-chunk streams through the drop-in API (global decode path) and the page container
+import gzip
+
+urls = gzip.open("tests/golden/urls.10K.gz").read()[:200000]
+c = cs.csnappy_compress(urls, 15)
+rc, outb = cs.csnappy_decompress(c, len(urls))
+assert rc == 0 and outb == urls
+h_in = np.frombuffer(urls, dtype=np.uint8).copy()
+cont = np.zeros(cs.api.bc_max_container_length(len(urls), 4096), dtype=np.uint8)
+clen = cs.api.bc_compress_host(h_in, len(urls), cont, 13, 4096)
+outp = np.zeros((len(urls) + 4095) // 4096 * 4096, dtype=np.uint8)
+rc, olen, _ = cs.api.bc_decompress_host(cont, clen, outp, 4096)
+assert rc == 0 and olen == len(urls) and outp[:olen].tobytes() == urls
+bad = bytes.fromhex("086162630104")
+assert cs.csnappy_decompress_noheader(bad, 100)[0] == -5
 print("sanitize_run ok")
