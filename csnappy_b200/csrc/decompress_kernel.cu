@@ -299,20 +299,42 @@ __device__ __forceinline__ int decode_batch(const Group<G> &g, const InBytes<GIN
 	// bytes, so "input exhausted", "long literal", "payload cut off" and "no space" all show up as a
 	// negative remainder and are told apart once, after the loop.  pos | produced << 16 advances with
 	// one packed add.
-	uint32_t state = st_pos | (st_produced << 16), ra = st_pos;
+	const uint32_t state0 = st_pos | (st_produced << 16);
+	const int irem0 = irem;
+	uint32_t state = state0, ra = st_pos;
 	uint32_t k = 0, e = 0;
+	// fast walk: per tag only the input remainder is tested; output space is tested for the batch as a whole
 #pragma unroll 8
 	for (; k < (uint32_t)G; ++k) {
 		e = lds_u32(lut_a + 4 * in.u8(GIN ? min(ra, last) : ra));
 		sts_u32(meta_a + 4 * k, state);
 		const uint32_t adv = e & 0xffffu;
-		const int x = irem - (int)adv, y = orem - (int)(e >> 16);
-		if ((x | y) < 0)
+		const int x = irem - (int)adv;
+		if (x < 0)
 			break;
 		state += e;
 		ra += adv;
 		irem = x;
-		orem = y;
+	}
+	if ((state >> 16) - st_produced <= (uint32_t)orem) {
+		orem -= (int)((state >> 16) - st_produced);
+	} else {
+		// the batch does not fit the output: walk it again with the per-tag space test to find the tag that fails
+		state = state0;
+		ra = st_pos;
+		irem = irem0;
+		for (k = 0; k < (uint32_t)G; ++k) {
+			e = lds_u32(lut_a + 4 * in.u8(GIN ? min(ra, last) : ra));
+			sts_u32(meta_a + 4 * k, state);
+			const uint32_t adv = e & 0xffffu;
+			const int x = irem - (int)adv, y = orem - (int)(e >> 16);
+			if ((x | y) < 0)
+				break;
+			state += e;
+			ra += adv;
+			irem = x;
+			orem = y;
+		}
 	}
 	uint32_t pos = state & 0xffffu, produced = state >> 16;
 	const uint32_t ntags = k;  // complete tags of this batch
