@@ -315,46 +315,52 @@ def main():
         d2h = payload + 4 * B + 8 * ((B + 8191) // 8192) + B * PAGE + 8 * B
         del h_in, h_cont, h_back
 
-    # ---- the alternative text class, short run (device-resident only) ---------------------
-    alt = None
+    # ---- short diagnostic runs (device-resident, rank 0's times): the alternative text class of SURVEY 8d, and
+    # ---- every page class of the main workload on its own ("report per-class and mixed") ----------
+    alt = per_class = None
     if not args.no_alt and not args.only:
-        other = "words" if args.text == "urls" else "urls"
         Ba = min(B, 1 << 18)
-        pa = synth.mixed_pages(Ba, PAGE, seed=SEED, device=dev, first_page=first, text=other)
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         a_comp = torch.empty(Ba * ostride, dtype=torch.uint8, device=dev)
         a_len = torch.empty(Ba, dtype=torch.int32, device=dev)
         a_back = torch.empty(Ba * PAGE, dtype=torch.uint8, device=dev)
         a_blen = torch.empty(Ba, dtype=torch.int32, device=dev)
         a_st = torch.empty(Ba, dtype=torch.int32, device=dev)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
 
-        def alt_step(record):
-            if record:
-                ev[0].record()
-            cs.batch_compress_fragments(pa, PAGE, Ba, WM, out=a_comp, out_len=a_len, out_stride=ostride)
-            if record:
-                ev[1].record()
-            cs.batch_decompress(a_comp, a_len, Ba, PAGE, in_stride=ostride, out=a_back, out_stride=PAGE,
-                                out_len=a_blen, status=a_st)
-            if record:
-                ev[2].record()
+        def short_run(pa, n):
+            def one(record):
+                if record:
+                    ev[0].record()
+                cs.batch_compress_fragments(pa, PAGE, n, WM, out=a_comp, out_len=a_len, out_stride=ostride)
+                if record:
+                    ev[1].record()
+                cs.batch_decompress(a_comp, a_len, n, PAGE, in_stride=ostride, out=a_back, out_stride=PAGE,
+                                    out_len=a_blen, status=a_st)
+                if record:
+                    ev[2].record()
 
-        for _ in range(3):
-            alt_step(False)
-        tca, tda = [], []
-        for _ in range(3):
-            alt_step(True)
-            torch.cuda.synchronize()
-            tca.append(ev[0].elapsed_time(ev[1]))
-            tda.append(ev[1].elapsed_time(ev[2]))
-        assert int((a_st != 0).sum()) == 0 and torch.equal(a_back, pa)
-        alt = {"text": TEXT_DESC[other], "pages_per_gpu": Ba,
-               "ratio": round(float(a_len.sum()) / (Ba * PAGE), 4),
-               "compress_gbs": round(world * Ba * PAGE / (statistics.mean(tca) * 1e-3) / 1e9, 2),
-               "decompress_gbs": round(world * Ba * PAGE / (statistics.mean(tda) * 1e-3) / 1e9, 2),
-               "value": round(2 * world * Ba * PAGE / ((statistics.mean(tca) + statistics.mean(tda)) * 1e-3) / 1e9, 2),
-               "note": "rank 0's times, mean of 3 steps after 3 warm-ups"}
-        del pa, a_comp, a_back
+            for _ in range(3):
+                one(False)
+            tc, td = [], []
+            for _ in range(3):
+                one(True)
+                torch.cuda.synchronize()
+                tc.append(ev[0].elapsed_time(ev[1]))
+                td.append(ev[1].elapsed_time(ev[2]))
+            assert int((a_st[:n] != 0).sum()) == 0 and torch.equal(a_back[: n * PAGE], pa)
+            tc, td = statistics.mean(tc) * 1e-3, statistics.mean(td) * 1e-3
+            return {"pages_per_gpu": n, "ratio": round(float(a_len[:n].sum()) / (n * PAGE), 4),
+                    "compress_gbs": round(world * n * PAGE / tc / 1e9, 2),
+                    "decompress_gbs": round(world * n * PAGE / td / 1e9, 2),
+                    "value": round(2 * world * n * PAGE / (tc + td) / 1e9, 2)}
+
+        other = "words" if args.text == "urls" else "urls"
+        alt = {"text": TEXT_DESC[other], "note": "rank 0's times, mean of 3 steps after 3 warm-ups",
+               **short_run(synth.mixed_pages(Ba, PAGE, seed=SEED, device=dev, first_page=first, text=other), Ba)}
+        Bc = min(B, 1 << 16)
+        per_class = {c: short_run(synth.mixed_pages(Bc, PAGE, seed=SEED, device=dev, first_page=first, text=args.text,
+                                                     only=c), Bc) for c in ("text", "zero", "random")}
+        del a_comp, a_back
 
     # ---- reduce over ranks: max time, sum bytes -------------------------------------------
     vals = torch.tensor([elapsed_ms, tc_ms, td_ms, e2e_ms or 0.0], dtype=torch.float64, device=dev)
@@ -409,6 +415,7 @@ def main():
         }
         if alt:
             line["alt_workload"] = alt
+            line["per_class"] = per_class
         if e2e_max:
             line["e2e"] = {"value": round(2 * total_n / (e2e_max * 1e-3) / 1e9, 2), "unit": "GB/s",
                            "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,

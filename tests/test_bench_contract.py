@@ -46,3 +46,6 @@ def test_b200_arm_line_on_gpu():
     assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and c["value"] > 0
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
     assert d["alt_workload"]["value"] > 0
+    # per-class ratios of the zram-style batch (text ~0.60, zero ~0.047, random ~1.001)
+    pc = d["per_class"]
+    assert 0.55 < pc["text"]["ratio"] < 0.65 and 0.04 < pc["zero"]["ratio"] < 0.055 and 1.0 < pc["random"]["ratio"] < 1.002
