@@ -23,6 +23,7 @@
 
 #define SLOT_STRIDE_32K 38272u /* csnappy_max_compressed_length(32768) = 38261, rounded up to 16 */
 #define HDR 16u		       /* device staging: [u32 out_len][i32 status][pad] then payload */
+#define SMALL_CALL 65536u      /* single calls up to this size take the one-synchronisation path */
 
 static __thread char tls_err[256];
 
@@ -285,6 +286,40 @@ static int64_t compress_host(const uint8_t *in, uint32_t n, uint8_t *out, int wm
 	pthread_mutex_lock(&C.mu);
 	TRY("stream create", ctx_init());
 	s = C.stream[0];
+	if (n_frag == 1) {
+		/* one fragment (the per-page call of zram / block_compressor): pinned bounce buffers, the size travels
+		 * in front of the slot, ONE stream synchronisation */
+		const size_t in_pad = ((size_t)n + 63) & ~(size_t)63, slot = HDR + csnappy_max_compressed_length(n);
+		uint8_t *pin;
+		uint32_t clen;
+		TRY("cudaMallocHost", grow_pin(&C.h_pin, in_pad + slot + 64));
+		TRY("cudaMalloc(in)", grow_dev(&C.d_in, (size_t)n + 64));
+		TRY("cudaMalloc(slots)", grow_dev(&C.d_out, SLOT_STRIDE_32K + HDR));
+		TRY("cudaMalloc(ctr)", grow_dev(&C.d_ctr, 64));
+		pin = (uint8_t *)C.h_pin.p;
+		memcpy(pin, in, n);
+		TRY("H2D", cudaMemcpyAsync(C.d_in.p, pin, n, cudaMemcpyHostToDevice, s));
+		memset(&a, 0, sizeof(a));
+		a.in = (const uint8_t *)C.d_in.p;
+		a.in_stride = CSB_FRAGMENT_MAX;
+		a.uniform_len = n;
+		a.n_blocks = 1;
+		a.out = (uint8_t *)C.d_out.p + HDR;
+		a.out_stride = SLOT_STRIDE_32K;
+		a.out_len = (uint32_t *)C.d_out.p;
+		a.wm = wm;
+		a.flags = framed ? CSNAPPY_BATCH_SHRINK_TABLE : 0;
+		a.lanes = g_compress_lanes;
+		a.ctas_per_sm = g_ctas_per_sm;
+		a.counter = (uint32_t *)C.d_ctr.p;
+		TRY("compress launch", csb_launch_compress(&a, (csb_stream_t)s));
+		TRY("D2H", cudaMemcpyAsync(pin + in_pad, C.d_out.p, slot, cudaMemcpyDeviceToHost, s));
+		TRY("sync", cudaStreamSynchronize(s));
+		memcpy(&clen, pin + in_pad, 4);
+		memcpy(out + hdr, pin + in_pad + HDR, clen);
+		rc = (int64_t)hdr + clen;
+		goto out;
+	}
 	TRY("cudaMalloc(in)", grow_dev(&C.d_in, (size_t)n + 64));
 	TRY("cudaMalloc(slots)", grow_dev(&C.d_out, (size_t)n_frag * SLOT_STRIDE_32K));
 	TRY("cudaMalloc(aux)", grow_dev(&C.d_aux, HDR + (size_t)n_frag * 4 + ((size_t)n_frag + 1) * 8 + 64));
@@ -305,15 +340,7 @@ static int64_t compress_host(const uint8_t *in, uint32_t n, uint8_t *out, int wm
 	a.ctas_per_sm = g_ctas_per_sm;
 	TRY("compress launch", csb_launch_compress(&a, (csb_stream_t)s));
 
-	if (n_frag == 1) {
-		/* one fragment: fetch its size, then exactly that many bytes */
-		uint32_t clen = 0;
-		TRY("D2H len", cudaMemcpyAsync(&clen, C.d_aux.p, 4, cudaMemcpyDeviceToHost, s));
-		TRY("sync", cudaStreamSynchronize(s));
-		TRY("D2H data", cudaMemcpyAsync(out + hdr, C.d_out.p, clen, cudaMemcpyDeviceToHost, s));
-		TRY("sync", cudaStreamSynchronize(s));
-		rc = (int64_t)hdr + clen;
-	} else {
+	{
 		uint64_t *d_off = (uint64_t *)((uint8_t *)C.d_aux.p + (((size_t)n_frag * 4 + 15) & ~(size_t)15));
 		uint64_t total = 0;
 		TRY("cudaMalloc(pack)", grow_dev(&C.d_pack, (size_t)n + (size_t)n / 6 + 32ull * n_frag + 64));
@@ -368,6 +395,48 @@ static int decompress_host(const uint8_t *src, uint32_t src_len, uint8_t *dst, u
 	pthread_mutex_lock(&C.mu);
 	TRY("stream create", ctx_init());
 	s = C.stream[0];
+	if (src_len <= SMALL_CALL && cap <= SMALL_CALL) {
+		/* one small block (the per-page call of zram / block_compressor): pinned bounce buffers, the input
+		 * length travels in front of the input and [out_len, status] in front of the output, ONE synchronisation */
+		const size_t in_bytes = HDR + src_len, in_pad = (in_bytes + 63) & ~(size_t)63, out_bytes = HDR + cap;
+		uint8_t *pin;
+		uint32_t *d_ihdr, *d_ohdr;
+		TRY("cudaMallocHost", grow_pin(&C.h_pin, in_pad + out_bytes + 64));
+		TRY("cudaMalloc(in)", grow_dev(&C.d_in, in_bytes + 64));
+		TRY("cudaMalloc(out)", grow_dev(&C.d_out, out_bytes + 64));
+		TRY("cudaMalloc(ctr)", grow_dev(&C.d_ctr, 64));
+		pin = (uint8_t *)C.h_pin.p;
+		memset(pin, 0, HDR);
+		memcpy(pin, &src_len, 4);
+		memcpy(pin + HDR, src, src_len);
+		TRY("H2D", cudaMemcpyAsync(C.d_in.p, pin, in_bytes, cudaMemcpyHostToDevice, s));
+		d_ihdr = (uint32_t *)C.d_in.p;
+		d_ohdr = (uint32_t *)C.d_out.p;
+		memset(&a, 0, sizeof(a));
+		a.in = (const uint8_t *)C.d_in.p + HDR;
+		a.in_len = d_ihdr;
+		a.n_blocks = 1;
+		a.out = (uint8_t *)C.d_out.p + HDR;
+		a.uniform_cap = cap;
+		a.out_len = d_ohdr;
+		a.status = (int32_t *)(d_ohdr + 1);
+		a.max_in_len = src_len;
+		a.lanes = g_decompress_lanes;
+		a.stage_input = g_stage_input;
+		a.smem_kb = g_smem_kb;
+		a.ctas_per_sm = g_ctas_per_sm;
+		a.counter = (uint32_t *)C.d_ctr.p;
+		TRY("decompress launch", csb_launch_decompress(&a, (csb_stream_t)s));
+		TRY("D2H", cudaMemcpyAsync(pin + in_pad, C.d_out.p, out_bytes, cudaMemcpyDeviceToHost, s));
+		TRY("sync", cudaStreamSynchronize(s));
+		memcpy(&res, pin + in_pad, 8);
+		rc = res.status;
+		if (rc == 0) {
+			memcpy(dst, pin + in_pad + HDR, res.out_len);
+			*produced = res.out_len;
+		}
+		goto out;
+	}
 	TRY("cudaMalloc(in)", grow_dev(&C.d_in, (size_t)src_len + 64));
 	TRY("cudaMalloc(out)", grow_dev(&C.d_out, (size_t)cap + 64));
 	TRY("cudaMalloc(aux)", grow_dev(&C.d_aux, 64));
