@@ -253,8 +253,13 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 				if (left < n)
 					n = (uint32_t)left;
 			}
-			if (n > p.in_cap)
-				n = p.in_cap;  // REQUIRES of the reference (csnappy.h:38): at most 32768, and never more than was staged for
+			if (n > p.in_cap) {
+				// REQUIRES of the reference (csnappy.h:38): at most 32768 bytes -- and never more than the staging
+				// area holds.  The reference has no error channel here; the batch has one: the size entry.
+				if (g.lane == 0)
+					a.out_len[blk] = CSB_LEN_REFUSED;
+				continue;
+			}
 			const uint8_t *src = a.in + in_at;
 			dst = a.out + (uint64_t)blk * a.out_stride;
 			// table size for this block (csnappy_compress.c:638-646 when SHRINK_TABLE is set)

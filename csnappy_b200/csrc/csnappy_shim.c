@@ -67,6 +67,8 @@ int csnappy_b200_set_tuning(const char *key, int value)
 		return 0;
 	}
 	if (!strcmp(key, "decompress_stage_input")) {
+		if (value < 0 || value > 4)
+			return CSNAPPY_E_BAD_ARG;
 		g_stage_input = value;
 		return 0;
 	}
@@ -581,6 +583,14 @@ int csnappy_batch_decompress_host(const void *h_in, uint64_t in_stride, const ui
 		return 0;
 	if (!h_in || !h_in_len || !h_out || !h_out_len || !h_status)
 		return set_err("null buffer", 0);
+	{
+		/* a length beyond the stride would make the kernel read past the staged chunk (csnappy_bc_decompress_host
+		 * checks its index the same way) */
+		uint32_t i;
+		for (i = 0; i < n_blocks; i++)
+			if (h_in_len[i] > in_stride)
+				return set_err("h_in_len[i] larger than in_stride", 0);
+	}
 
 	pthread_mutex_lock(&C.mu);
 	TRY("stream create", ctx_init());

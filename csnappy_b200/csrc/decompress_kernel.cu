@@ -34,7 +34,8 @@ namespace csb {
 
 constexpr int E_OK = 0, E_HEADER_BAD = -1, E_OUTPUT_INSUF = -2, E_OUTPUT_OVERRUN = -3, E_DATA_MALFORMED = -5;
 constexpr int kMaxThreadsD = 832;
-constexpr int kMinStagedGroups = 8;  // fewer staged blocks per SM than this: use the global path instead
+constexpr int kMinStagedGroups = 8;
+constexpr uint32_t kLaneMinBlocks = 8192;  // unstaged batches at least this large go one lane per block  // fewer staged blocks per SM than this: use the global path instead
 
 
 struct DecompressParams {
@@ -597,7 +598,7 @@ __global__ void __launch_bounds__(kMaxThreadsD, 1) decompress_kernel(const Decom
 					ilen -= used;
 				}
 			}
-			if (rc == E_OK && !((GIN || ilen + 32 <= p.in_area) && cap <= p.out_area && ilen < 65536u)) {
+			if (rc == E_OK && !((GIN || ilen + 32 <= p.in_area) && cap <= p.out_area && ilen < 65535u)) {  // 0xffff is the walk's long-literal marker: a staged block is shorter
 				uint32_t produced = 0;
 				if ((a.flags & 4u) && ilen == cap) {  // stored block too large to stage: plain copy
 					for (uint32_t i = g.lane; i < ilen; i += G)
@@ -758,7 +759,16 @@ extern "C" int csb_launch_decompress(const struct csb_decompress_args *a, csb_st
 	const int max_groups = kMaxThreadsD / G;
 	if (groups > max_groups)
 		groups = max_groups;
-	if ((groups < kMinStagedGroups && a->stage_input != 1) || a->stage_input == 3) {
+	const bool unstaged = (groups < kMinStagedGroups && a->stage_input != 1) || a->stage_input == 3 || groups < 1;
+	// One lane per block (decompress_lane_kernel.cu) when the blocks would not be staged and there are enough of
+	// them to fill the machine with lanes; needs 8-byte aligned output slots.
+	const bool lane_ok = ((reinterpret_cast<uintptr_t>(a->out) | a->out_stride) & 7u) == 0;
+	if (a->stage_input == 4 || (unstaged && a->stage_input == 0 && lane_ok && a->n_blocks >= kLaneMinBlocks)) {
+		if (!lane_ok)
+			return (int)cudaErrorMisalignedAddress;
+		return csb_launch_decompress_lane(a, s);
+	}
+	if (unstaged) {
 		// too few blocks fit shared memory for their chains to hide each other: global path, one group per warp slot
 		p.in_area = p.out_area = 0;
 		p.group_smem = meta_bytes;

@@ -14,12 +14,14 @@ extern "C" {
 typedef struct CUstream_st *csb_stream_t; /* == cudaStream_t */
 
 #define CSB_FRAGMENT_MAX 32768u
+#define CSB_LEN_REFUSED 0xffffffffu /* == CSNAPPY_BATCH_LEN_REFUSED */
 
 struct csb_compress_args {
 	const uint8_t *in;
 	const uint64_t *in_off; /* NULL => i * in_stride */
 	uint64_t in_stride;
-	const uint32_t *in_len; /* NULL => uniform_len (clipped by total_len if nonzero) */
+	const uint32_t *in_len; /* NULL => uniform_len (clipped by total_len if nonzero); an entry above 32768 or above
+				   the stride is refused: out_len[i] = CSB_LEN_REFUSED, nothing written */
 	uint32_t uniform_len;
 	uint64_t total_len;	/* nonzero: block i has min(uniform_len, total_len - i*in_stride) bytes */
 	uint32_t n_blocks;
@@ -30,7 +32,7 @@ struct csb_compress_args {
 	uint32_t flags;		/* CSNAPPY_BATCH_SHRINK_TABLE */
 	int lanes;		/* lanes cooperating on one block: 8, 16, 32 (0 = default) */
 	int ctas_per_sm;	/* 0 = default */
-	uint32_t *counter;	/* device word for the block claim counter (NULL: stream-ordered allocation per launch) */
+	uint32_t *counter;	/* device word for the block claim counter (NULL: a word of the per-device ring, pack_kernel.cu next_counter) */
 };
 
 struct csb_decompress_args {
@@ -49,14 +51,16 @@ struct csb_decompress_args {
 	uint32_t max_in_len;	/* staging hint: longest input block (0 = derive) */
 	int lanes;
 	int ctas_per_sm;
-	uint32_t *counter;	/* device word for the block claim counter (NULL: stream-ordered allocation per launch) */
-	int stage_input;	/* 2: read the compressed block through L1; else stage it in shared memory */
+	uint32_t *counter;	/* device word for the block claim counter (NULL: a word of the per-device ring, pack_kernel.cu next_counter) */
+	int stage_input;	/* 0: choose; 1: always stage in shared memory; 2: stage only the output; 3: warp per block against
+				   global memory; 4: one lane per block (decompress_lane_kernel.cu) */
 	int smem_kb;		/* unstaged mode: shared memory to use per SM, rest stays L1 (0 = default) */
 };
 
 /* all return 0 or a cudaError_t value (> 0) */
 int csb_launch_compress(const struct csb_compress_args *a, csb_stream_t s);
 int csb_launch_decompress(const struct csb_decompress_args *a, csb_stream_t s);
+int csb_launch_decompress_lane(const struct csb_decompress_args *a, csb_stream_t s); /* one lane per block; out and out_stride 8-byte aligned */
 int csb_launch_pack(const uint8_t *slots, uint64_t slot_stride, const uint32_t *len,
 		    uint32_t n_blocks, uint8_t *packed, uint64_t *off, csb_stream_t s);
 int csb_launch_pack_stored(const uint8_t *slots, uint64_t slot_stride, const uint32_t *len, uint32_t n_blocks,

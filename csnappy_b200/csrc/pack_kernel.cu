@@ -43,8 +43,11 @@ int device_info(DeviceInfo *out)
 
 // Block-claim counters: a per-device ring of device words handed out round-robin, so a launch never
 // allocates (a stream-ordered allocation per launch showed up as milliseconds of launch jitter).
-// A slot is reused after kCounterSlots further launches on this device -- far more than can be in flight.
-constexpr unsigned kCounterSlots = 4096;
+// A slot is reused after kCounterSlots further launches on this device.  LIMIT: a kernel still running when
+// 65536 later launches (on other streams of the same device) have been issued would share its counter with a
+// new launch; the host-side launch rate (~5 us per launch) makes that a kernel running for > 0.3 s next to a
+// stream issuing launches back to back -- the batched callers in csnappy_shim.c pass their own counters instead.
+constexpr unsigned kCounterSlots = 65536;
 uint32_t *next_counter()
 {
 	static std::mutex mu;

@@ -50,8 +50,12 @@ extern "C" {
  * Batched csnappy_compress_fragment (csnappy_compress.c:469-606).
  *   d_in_len == NULL  => every block is uniform_in_len bytes.
  *   d_out_len[i]      <- compressed size of block i.
- * Block lengths must be <= 32768; 9 <= wm <= 16.
+ * Block lengths must be <= 32768 (and <= in_stride when strided); 9 <= wm <= 16.
+ * The reference has no error channel on this side (csnappy.h:38 only REQUIRES it); here a
+ * d_in_len[i] that breaks the rule is refused: d_out_len[i] = CSNAPPY_BATCH_LEN_REFUSED and
+ * nothing is written to the block's slot.
  */
+#define CSNAPPY_BATCH_LEN_REFUSED 0xffffffffu
 int csnappy_batch_compress_fragments(const void *d_in, const uint64_t *d_in_off,
 				     uint64_t in_stride, const uint32_t *d_in_len,
 				     uint32_t uniform_in_len, uint32_t n_blocks,

@@ -187,7 +187,7 @@ def test_batch_compress_shrink_table_flag(cs, chk):
         assert got == chk.compress_fragment(text[:n], oracle.port().chunk_wm(n, 16)), n
 
 
-@pytest.mark.parametrize("stage", [0, 2])
+@pytest.mark.parametrize("stage", [0, 2, 4])
 @pytest.mark.parametrize("lanes", [32, 16, 8])
 def test_batch_decompress_roundtrip_and_errors(cs, chk, lanes, stage):
     pages = fuzz_pages(99, 140, 4096)
@@ -229,8 +229,10 @@ def test_batch_decompress_roundtrip_and_errors(cs, chk, lanes, stage):
     assert n_err > 20
 
 
-def test_batch_decompress_with_header_and_streaming_path(cs, chk, urls, urls_snappy, baddata3, unaligned_pair):
-    """Whole multi-chunk streams in one batch: exercises the global-memory path and -1/-2."""
+@pytest.mark.parametrize("stage", [0, 4])
+def test_batch_decompress_with_header_and_streaming_path(cs, chk, urls, urls_snappy, baddata3, unaligned_pair, stage):
+    """Whole multi-chunk streams in one batch: exercises the global-memory path (stage 0: a warp per stream,
+    stage 4: a lane per stream) and -1/-2."""
     uu_s, uu_b = unaligned_pair
     streams = [urls_snappy, baddata3, uu_s, b"", bytes.fromhex("80"), chk.compress(urls[:5000], 16), urls_snappy]
     caps = [len(urls), 130378, len(uu_b), 10, 10, 5000, 4096]
@@ -248,9 +250,13 @@ def test_batch_decompress_with_header_and_streaming_path(cs, chk, urls, urls_sna
     d_len = torch.tensor([len(s) for s in streams], dtype=torch.int32).cuda()
     d_caps = torch.tensor(caps, dtype=torch.int32).cuda()
     ostride = (max(caps) + 15) // 16 * 16
-    out, out_len, status = cs.batch_decompress(d_in, d_len, len(streams), 0, in_off=d_off, out_caps=d_caps,
-                                               out_stride=ostride, flags=cs.api.BATCH_WITH_HEADER)
-    torch.cuda.synchronize()
+    cs.set_tuning("decompress_stage_input", stage)
+    try:
+        out, out_len, status = cs.batch_decompress(d_in, d_len, len(streams), 0, in_off=d_off, out_caps=d_caps,
+                                                   out_stride=ostride, flags=cs.api.BATCH_WITH_HEADER)
+        torch.cuda.synchronize()
+    finally:
+        cs.set_tuning("decompress_stage_input", 0)
     st, ol, o = status.cpu().numpy(), out_len.cpu().numpy(), out.cpu().numpy()
     assert list(st) == expect_rc
     assert o[: ol[0]].tobytes() == urls
@@ -364,14 +370,16 @@ def test_batch_decompress_raw_if_full_flag(cs, chk):
     d_in = torch.from_numpy(host).cuda()
     d_off = torch.from_numpy(off[:-1].astype(np.int64)).cuda()
     d_len = torch.tensor([len(s) for s in streams], dtype=torch.int32).cuda()
-    for lanes in (8, 16, 32):
+    for lanes in (8, 16, 32, 0):
         cs.set_tuning("decompress_lanes", lanes)
+        cs.set_tuning("decompress_stage_input", 0 if lanes else 4)  # last round: one lane per block
         try:
             out, out_len, status = cs.batch_decompress(d_in, d_len, len(streams), page, in_off=d_off, out_stride=page,
                                                        flags=cs.api.BATCH_RAW_IF_FULL)
             torch.cuda.synchronize()
         finally:
             cs.set_tuning("decompress_lanes", 0)
+            cs.set_tuning("decompress_stage_input", 0)
         o = out.cpu().numpy()
         assert status.cpu().tolist() == [0, 0, 0, 0] and out_len.cpu().tolist() == [page] * 4
         for i, e in enumerate(expect):

@@ -23,9 +23,10 @@ def timed(fn, reps=3):
 
 
 stage = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+scale = int(sys.argv[2]) if len(sys.argv) > 2 else 1  # multiplies the number of blocks (1: 0.5 GiB per shape)
 cs.set_tuning("decompress_stage_input", stage)
 print("decompress_stage_input", stage)
-for L, wm, n in ((32768, 15, 16384), (32768, 16, 16384), (16384, 14, 32768), (4096, 13, 131072)):
+for L, wm, n in ((32768, 15, 16384 * scale), (32768, 16, 16384 * scale), (16384, 14, 32768 * scale), (4096, 13, 131072 * scale)):
     d = synth.text_fragments(n, L, device="cuda")
     ostride = cs.api.out_stride_for(L)
     out = torch.empty(n * ostride, dtype=torch.uint8, device="cuda")
