@@ -34,8 +34,7 @@ namespace csb {
 
 constexpr int E_OK = 0, E_HEADER_BAD = -1, E_OUTPUT_INSUF = -2, E_OUTPUT_OVERRUN = -3, E_DATA_MALFORMED = -5;
 constexpr int kMaxThreadsD = 832;
-constexpr int kMinStagedGroups = 8;
-constexpr uint32_t kLaneMinBlocks = 8192;  // unstaged batches at least this large go one lane per block  // fewer staged blocks per SM than this: use the global path instead
+constexpr int kMinStagedGroups = 8;  // fewer staged blocks per SM than this: use the global path instead
 
 
 struct DecompressParams {
@@ -760,10 +759,13 @@ extern "C" int csb_launch_decompress(const struct csb_decompress_args *a, csb_st
 	if (groups > max_groups)
 		groups = max_groups;
 	const bool unstaged = (groups < kMinStagedGroups && a->stage_input != 1) || a->stage_input == 3 || groups < 1;
-	// One lane per block (decompress_lane_kernel.cu) when the blocks would not be staged and there are enough of
-	// them to fill the machine with lanes; needs 8-byte aligned output slots.
-	const bool lane_ok = ((reinterpret_cast<uintptr_t>(a->out) | a->out_stride) & 7u) == 0;
-	if (a->stage_input == 4 || (unstaged && a->stage_input == 0 && lane_ok && a->n_blocks >= kLaneMinBlocks)) {
+	// One lane per block (decompress_lane_kernel.cu) when there are enough blocks to fill the machine with lanes
+	// (1280 per SM): measured crossovers on a B200 are ~24 Ki blocks against the warp-per-block global path
+	// (32 KiB fragments: 116 vs 77 GB/s at 32 Ki, 300 vs 77 at 128 Ki) and ~150 Ki blocks against the staged path
+	// (mixed 4 KiB pages: 408 vs 417 GB/s at 128 Ki, 538 vs 430 at 256 Ki).  Needs 16-byte aligned output slots.
+	const bool lane_ok = ((reinterpret_cast<uintptr_t>(a->out) | a->out_stride) & 15u) == 0;
+	const uint32_t lane_min = (uint32_t)di.sm_count * (unstaged ? 160u : 1100u);
+	if (a->stage_input == 4 || (a->stage_input == 0 && lane_ok && a->n_blocks >= lane_min)) {
 		if (!lane_ok)
 			return (int)cudaErrorMisalignedAddress;
 		return csb_launch_decompress_lane(a, s);

@@ -2,29 +2,32 @@
 //
 // Second decoder family next to decompress_kernel.cu, for blocks that do not fit shared memory in useful
 // numbers (32 KiB fragments and anything larger: 3 staged fragments per SM, or 26 warp-owned blocks on
-// the global path).  A block's tag stream is a serial chain whose step costs an L2 round trip once the
-// block lives in global memory; the only way to hide that is MANY chains, and a lane is the cheapest
-// owner a chain can have: 1024 blocks in flight per SM instead of 26.  Each lane runs the reference's
-// loop (csnappy_decompress.c:345-382) literally -- tag, length, checks, copy -- on its own block:
+// the global path) and for very large batches of small blocks.  A block's tag stream is a serial chain
+// whose step costs an L2 round trip once the block lives in global memory; the only way to hide that
+// is MANY chains, and a lane is the cheapest owner a chain can have: 1280 blocks in flight per SM
+// instead of 26.  Each lane runs the reference's loop (csnappy_decompress.c:345-382) -- tag, length,
+// checks, copy -- on its own block:
 //
-//   * ONE load path for the tag stream, literal payloads and back-references: the two aligned 8-byte
-//     words around the (arbitrarily aligned) source and a funnel shift; output through an 8-byte
-//     accumulator flushed with aligned 8-byte stores, so every memory instruction moves 8 bytes per
-//     lane whatever the alignment of the tag;
+//   * ONE load path for the tag stream, literal payloads and back-references: the two aligned 16-byte
+//     vectors around the (arbitrarily aligned) source and a funnel shift; output through a 16-byte
+//     accumulator flushed with aligned 16-byte stores, so every memory instruction moves 16 bytes per
+//     lane whatever the alignment of the tag, and most tags (mean length 12-14 bytes) need ONE move;
 //   * back-references read the lane's own earlier stores (same thread, same address: ordered); the
 //     not yet stored tail of the accumulator is flushed first when a copy reaches into it
-//     (offset < 15), and offsets 1, 2 and 4 are expanded in registers (pattern fill);
+//     (offset < 31), and offsets 1, 2, 4 and 8 are expanded in registers (pattern fill);
 //   * the loop is FLAT and WARP-UNIFORM: one iteration = claim (free lanes take the next block from
-//     the global counter) / tag (lanes whose tag is used up decode the next) / move (every lane moves
-//     up to 8 bytes), with a reconvergence point between the phases -- without them the lanes of a
-//     warp drift apart and run the loop body one lane at a time (measured: 6.7 of 32 lanes active).
+//     the global counter) / tag (lanes whose tag is used up decode the next, with selects instead of
+//     branches between the tag kinds) / bulk (long literals are copied by the whole warp) / move
+//     (every lane moves up to 16 bytes), with a reconvergence point between the phases -- without
+//     them the lanes of a warp drift apart and run the loop body one lane at a time (measured: 6.7
+//     of 32 lanes active per instruction, 121 GB/s instead of 272 on 32 KiB fragments).
 //
 // Semantics per block are those of decompress_kernel.cu: first failing tag in stream order decides;
 // literal: input shortage (-5) before space (-3); copy: offset validity (-5) before space (-3); end of
 // input at a tag boundary is success; a tag header cut off by the end of input is -5 (defined here,
 // SURVEY.md 0.5); nothing is ever written at or past the block's capacity.
-// The kernel is bound by the LSU (a fully divergent 8-byte access costs ~2 cycles per lane), not by
-// HBM; see DESIGN.md 4.3.
+// Needs 16-byte aligned output slots (out, out_stride).  Bound by instruction issue and the LSU (a
+// fully divergent access costs ~2 cycles per lane), not by HBM; see DESIGN.md 4.3.
 #include "device_common.cuh"
 #include "kernels.h"
 
@@ -32,36 +35,60 @@ namespace csb {
 
 constexpr int L_OK = 0, L_HEADER_BAD = -1, L_OUTPUT_INSUF = -2, L_OUTPUT_OVERRUN = -3, L_DATA_MALFORMED = -5;
 constexpr int kLaneThreads = 256;
+constexpr uint32_t kBulkMin = 528;  // literals at least this long leave the lane loop for a warp-wide copy
 
-__device__ __forceinline__ uint64_t ldg64(uintptr_t a)
+struct U128 {
+	uint64_t lo, hi;
+};
+
+__device__ __forceinline__ U128 ldg128(uintptr_t a)
 {
-	uint64_t v;
-	asm volatile("ld.global.u64 %0, [%1];" : "=l"(v) : "l"(a) : "memory");
+	U128 v;
+	asm volatile("ld.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.lo), "=l"(v.hi) : "l"(a) : "memory");
 	return v;
 }
-__device__ __forceinline__ void stg64(uintptr_t a, uint64_t v)
+__device__ __forceinline__ void stg128(uintptr_t a, uint64_t lo, uint64_t hi)
 {
-	asm volatile("st.global.u64 [%0], %1;" ::"l"(a), "l"(v) : "memory");
+	asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(a), "l"(lo), "l"(hi) : "memory");
+}
+// (hi:lo) >> 8 r for r in 0..7, without the undefined shift by 64
+__device__ __forceinline__ uint64_t shr_pair(uint64_t lo, uint64_t hi, uint32_t r)
+{
+	return (lo >> (8u * r)) | ((hi << 1) << (63u - 8u * r));
 }
 
-// `need` (1..8) bytes at byte address a, little endian, without touching a byte at or past `lim`.
+// `need` (1..16) bytes at byte address a, little endian, without touching a byte at or past `lim`.
 // One code path for the tag stream, literal payloads (lim = end of the block) and back-references
-// (lim = end of the output slot): two aligned words and a funnel shift.  A word that starts before
-// the block still lies inside the caller's allocation (allocations are 256-byte aligned).
-__device__ __forceinline__ uint64_t load8(uintptr_t a, uint32_t need, uintptr_t lim)
+// (lim = end of the output slot): the two aligned vectors around a and a funnel shift.  A vector that
+// starts before the block still lies inside the caller's allocation (allocations are 256-byte aligned).
+__device__ __forceinline__ U128 load16(uintptr_t a, uint32_t need, uintptr_t lim)
 {
-	const uintptr_t w = a & ~(uintptr_t)7;
-	const uint32_t k = (uint32_t)a & 7u;
-	if (w + 16 <= lim) {
-		const uint64_t lo = ldg64(w);
-		if (k + need <= 8)
-			return lo >> (8u * k);
-		return (lo >> (8u * k)) | (ldg64(w + 8) << (64u - 8u * k));
+	const uintptr_t w = a & ~(uintptr_t)15;
+	const uint32_t k = (uint32_t)a & 15u;
+	const bool two = k + need > 16;
+	U128 r;
+	if (w + (two ? 32 : 16) <= lim) {
+		const U128 A = ldg128(w);
+		U128 B;
+		B.lo = B.hi = 0;
+		if (two)
+			B = ldg128(w + 16);
+		const bool q = k >= 8;
+		const uint32_t s = k & 7u;
+		const uint64_t x0 = q ? A.hi : A.lo, x1 = q ? B.lo : A.hi, x2 = q ? B.hi : B.lo;
+		r.lo = shr_pair(x0, x1, s);
+		r.hi = shr_pair(x1, x2, s);
+		return r;
 	}
-	uint64_t v = 0;	 // the last words of the block / slot: byte by byte
-	for (uint32_t i = 0; i < need && a + i < lim; ++i)
-		v |= (uint64_t) * reinterpret_cast<const volatile uint8_t *>(a + i) << (8 * i);
-	return v;
+	r.lo = r.hi = 0;  // the last bytes of the block / slot: byte by byte
+	for (uint32_t i = 0; i < need && a + i < lim; ++i) {
+		const uint64_t b = *reinterpret_cast<const volatile uint8_t *>(a + i);
+		if (i < 8)
+			r.lo |= b << (8 * i);
+		else
+			r.hi |= b << (8 * (i - 8));
+	}
+	return r;
 }
 
 struct LaneParams {
@@ -71,20 +98,29 @@ struct LaneParams {
 
 enum : uint32_t { M_LIT = 0, M_COPY = 1, M_PATTERN = 2, M_NEAR = 3 };
 
-// The loop is warp-uniform: every iteration has a CLAIM phase (lanes without a block take the next one
-// from the global counter), a TAG phase (lanes whose tag is used up decode the next one; a lane whose
-// block ends here stores its result and becomes free) and a MOVE phase (every lane moves up to 8 bytes
-// of its current tag), with the lanes reconverging between the phases.  Literals, back-references and
-// the tag stream share ONE load path (load8), so the MOVE phase is free of mode-dependent branches
-// except for the rare pattern / near-offset cases.
+// make the accumulator's bytes [op & ~15, op) visible to this lane's loads
+__device__ __forceinline__ void flush_partial(uintptr_t dst, uint32_t cap, uint32_t op, uint64_t acc0, uint64_t acc1)
+{
+	const uint32_t k = op & 15u, w = op & ~15u;
+	if (!k)
+		return;
+	if (w + 16 <= cap) {
+		stg128(dst + w, acc0, acc1);  // upper bytes: zeros inside the capacity, rewritten later
+	} else {
+		for (uint32_t i = 0; i < k; ++i)
+			*reinterpret_cast<volatile uint8_t *>(dst + w + i) = (uint8_t)((i < 8 ? acc0 : acc1) >> (8 * (i & 7u)));
+	}
+}
+
 __global__ void __launch_bounds__(kLaneThreads) decompress_lane_kernel(const LaneParams p)
 {
 	const csb_decompress_args &a = p.a;
 	const unsigned full = 0xffffffffu;
+	const uint32_t lane = threadIdx.x & 31u;
 	bool have = false, more = true;
 	uint32_t blk = 0, cap = 0, ip = 0, op = 0, rem = 0, mode = M_LIT, off = 0;
 	uintptr_t src = 0, src_end = 0, dst = 0;
-	uint64_t acc = 0, pat = 0;  // acc: bytes [op & ~7, op) of the output, not yet stored
+	uint64_t acc0 = 0, acc1 = 0, pat = 0;  // acc: bytes [op & ~15, op) of the output, not yet stored
 
 	for (;;) {
 		// ---- CLAIM ----
@@ -127,7 +163,7 @@ __global__ void __launch_bounds__(kLaneThreads) decompress_lane_kernel(const Lan
 					src = reinterpret_cast<uintptr_t>(s);
 					src_end = src + ilen;
 					ip = op = rem = 0;
-					acc = 0;
+					acc0 = acc1 = 0;
 					mode = M_LIT;
 					if ((a.flags & 4u) && ilen == cap)
 						rem = ilen;  // stored block (block_compressor.c:378): the whole input is one literal payload
@@ -140,136 +176,120 @@ __global__ void __launch_bounds__(kLaneThreads) decompress_lane_kernel(const Lan
 
 		// ---- TAG: next tag of the reference's loop (csnappy_decompress.c:345-382) ----
 		if (have && rem == 0) {
-			int rc = L_OK;
-			bool fin = false;
 			const uint32_t ilen = (uint32_t)(src_end - src);
-			if (ip >= ilen) {
-				fin = true;  // end of input at a tag boundary
-			} else {
+			int rc = L_OK;
+			const bool fin = ip >= ilen;  // end of input at a tag boundary
+			if (!fin) {
 				const uint32_t left = ilen - ip;
-				const uint64_t x = load8(src + ip, left < 8 ? left : 8u, src_end);
-				const uint32_t tag = (uint32_t)x & 0xffu, kind = tag & 3u;
-				uint32_t len = (tag >> 2) + 1;
-				if (kind == 0) {
-					uint32_t hdr = 1;
-					if (len > 60) {
-						const uint32_t nb = len - 60;
-						if (left - 1 < nb) {
-							rc = L_DATA_MALFORMED;	// length bytes cut off (reference: UB)
-						} else {
-							const uint32_t v = (uint32_t)(x >> 8) & (nb == 4 ? 0xffffffffu : ((1u << (8 * nb)) - 1u));
-							len = v + 1;  // 0xffffffff wraps to a zero-length literal (csnappy_decompress.c:370)
-							hdr = 1 + nb;
-						}
-					}
-					if (rc == L_OK) {
-						ip += hdr;
-						// (a length of 2^31 or more passes the reference's signed input check and fails on space, :374)
-						if ((int32_t)len >= 0 ? (ilen - ip < len) : (cap - op >= len))
-							rc = L_DATA_MALFORMED;
-						else if (cap - op < len)
-							rc = L_OUTPUT_OVERRUN;
-						mode = M_LIT;
-						rem = len;
-					}
-				} else {
-					const uint32_t hdr = kind == 1 ? 2u : (kind == 2 ? 3u : 5u);
-					if (left < hdr) {
-						rc = L_DATA_MALFORMED;	// offset bytes cut off (reference: UB)
-					} else {
-						if (kind == 1) {
-							len = ((tag >> 2) & 7u) + 4;
-							off = ((tag >> 5) << 8) | ((uint32_t)(x >> 8) & 0xffu);
-						} else if (kind == 2) {
-							off = (uint32_t)(x >> 8) & 0xffffu;
-						} else {
-							off = (uint32_t)(x >> 8);
-						}
-						ip += hdr;
-						if (off - 1u >= op)  // off == 0 or off > produced, csnappy_decompress.c:302
-							rc = L_DATA_MALFORMED;
-						else if (cap - op < len)
-							rc = L_OUTPUT_OVERRUN;
-						rem = len;
-						// off >= 15: the source never reaches into the unstored accumulator
-						mode = off >= 15 ? M_COPY : ((off == 1 || off == 2 || off == 4) ? M_PATTERN : M_NEAR);
-					}
-				}
-			}
-			if (rc == L_OK && !fin && mode >= M_PATTERN && rem) {
-				// make bytes [op & ~7, op) visible to this lane's loads
-				const uint32_t k = op & 7u, w = op & ~7u;
-				if (k) {
-					if (w + 8 <= cap) {
-						stg64(dst + w, acc);  // upper bytes: zeros inside the capacity, rewritten later
-					} else {
-						for (uint32_t i = 0; i < k; ++i)
-							*reinterpret_cast<volatile uint8_t *>(dst + w + i) = (uint8_t)(acc >> (8 * i));
-					}
-				}
-				if (mode == M_PATTERN) {
-					pat = load8(dst + op - off, off, dst + cap);
-					if (off == 1)
-						pat = (pat & 0xffull) * 0x0101010101010101ull;
-					else if (off == 2)
-						pat = (pat & 0xffffull) * 0x0001000100010001ull;
-					else
-						pat = (pat & 0xffffffffull) * 0x0000000100000001ull;
-				}
+				const uint64_t x = load16(src + ip, left < 8 ? left : 8u, src_end).lo;
+				const uint32_t tag = (uint32_t)x & 0xffu, kind = tag & 3u, lf = tag >> 2;
+				const uint32_t extra = (uint32_t)(x >> 8);
+				const bool lit = kind == 0, longlit = lit && lf >= 60;
+				// header bytes: literal 1 (+ 1..4 length bytes), copy 2 / 3 / 5
+				const uint32_t hdr = lit ? (longlit ? lf - 58u : 1u) : (kind == 1 ? 2u : (kind == 2 ? 3u : 5u));
+				const uint32_t nb8 = 8u * (lf - 59u);  // bits of the long literal's length field
+				const uint32_t lv = longlit ? (extra & (nb8 >= 32 ? 0xffffffffu : ((1u << (nb8 & 31u)) - 1u))) : lf;
+				// literal: length field + 1 (0xffffffff wraps to a zero-length literal, csnappy_decompress.c:370)
+				const uint32_t len = kind == 1 ? ((lf & 7u) + 4u) : (lv + 1u);
+				off = kind == 1 ? (((tag >> 5) << 8) | (extra & 0xffu)) : (kind == 2 ? (extra & 0xffffu) : extra);
+				const uint32_t ip2 = ip + hdr, room = cap - op;
+				// check order of the reference: header / length bytes present (UB there, -5 here); literal: input
+				// shortage (a length of 2^31 or more passes its signed test and fails on space, :374) then space;
+				// copy: offset == 0 or > produced (:302) then space
+				const bool cut = left < hdr;
+				const bool bad = lit ? ((int32_t)len >= 0 ? (ilen - ip2 < len) : (room >= len)) : (off - 1u >= op);
+				rc = (cut || bad) ? L_DATA_MALFORMED : (room < len ? L_OUTPUT_OVERRUN : L_OK);
+				ip = ip2;
+				rem = len;
+				// copies: off >= 31 never reaches into the unstored accumulator
+				mode = lit ? M_LIT : (off >= 31 ? M_COPY : ((off == 1 || off == 2 || off == 4 || off == 8) ? M_PATTERN : M_NEAR));
 			}
 			if (rc != L_OK || fin) {
-				if (rc == L_OK) {
-					const uint32_t k = op & 7u, w = op & ~7u;
-					if (k) {
-						if (w + 8 <= cap) {
-							stg64(dst + w, acc);
-						} else {
-							for (uint32_t i = 0; i < k; ++i)
-								*reinterpret_cast<volatile uint8_t *>(dst + w + i) = (uint8_t)(acc >> (8 * i));
-						}
-					}
-				}
+				if (rc == L_OK)
+					flush_partial(dst, cap, op, acc0, acc1);
 				a.status[blk] = rc;
 				a.out_len[blk] = rc == L_OK ? op : 0u;
 				have = false;
 				rem = 0;
+			} else if (mode == M_PATTERN && rem) {
+				flush_partial(dst, cap, op, acc0, acc1);
+				pat = load16(dst + op - off, off, dst + cap).lo;
+				if (off == 1)
+					pat = (pat & 0xffull) * 0x0101010101010101ull;
+				else if (off == 2)
+					pat = (pat & 0xffffull) * 0x0001000100010001ull;
+				else if (off == 4)
+					pat = (pat & 0xffffffffull) * 0x0000000100000001ull;
 			}
 		}
 		__syncwarp(full);
 
-		// ---- MOVE: up to 8 bytes of the current tag ----
+		// ---- BULK: a long literal (incompressible data, stored blocks) is copied by the whole warp ----
+		// once the owner's output position is 16-byte aligned (the MOVE phase below aligns it first)
+		unsigned bulk = __ballot_sync(full, have && mode == M_LIT && rem >= kBulkMin && (op & 15u) == 0);
+		while (bulk) {
+			const int o = __ffs(bulk) - 1;
+			bulk &= bulk - 1;
+			const uintptr_t s_ = __shfl_sync(full, (unsigned long long)(src + ip), o);
+			const uintptr_t d_ = __shfl_sync(full, (unsigned long long)(dst + op), o);
+			const uintptr_t lim = __shfl_sync(full, (unsigned long long)src_end, o);
+			const uint32_t n_ = __shfl_sync(full, rem & ~15u, o);
+			for (uint32_t i = 16 * lane; i < n_; i += 512) {
+				const U128 v = load16(s_ + i, 16, lim);
+				stg128(d_ + i, v.lo, v.hi);
+			}
+			if ((int)lane == o) {
+				ip += n_;
+				op += n_;
+				rem -= n_;
+			}
+		}
+		__syncwarp(full);
+
+		// ---- MOVE: up to 16 bytes of the current tag ----
 		if (have && rem) {
-			uint32_t n = rem < 8 ? rem : 8;
-			uint64_t v = pat;
+			uint32_t n = rem < 16 ? rem : 16;
+			if (mode == M_LIT && rem >= kBulkMin)
+				n = 16 - (op & 15u);  // align the output for the bulk copy (16 when it already is: never here)
+			U128 v;
+			v.lo = v.hi = pat;
 			if (mode == M_NEAR) {
-				// offsets 3, 5..14: rounds of at most `off` bytes read only what is already there; the
+				// offsets 3, 5..7, 9..30: rounds of at most `off` bytes read only what is already there; the
 				// accumulator's bytes must be in memory first
 				if (n > off)
 					n = off;
-				const uint32_t k = op & 7u, w = op & ~7u;
-				if (k) {
-					if (w + 8 <= cap) {
-						stg64(dst + w, acc);
-					} else {
-						for (uint32_t i = 0; i < k; ++i)
-							*reinterpret_cast<volatile uint8_t *>(dst + w + i) = (uint8_t)(acc >> (8 * i));
-					}
-				}
+				flush_partial(dst, cap, op, acc0, acc1);
 			}
 			if (mode != M_PATTERN) {
 				const bool lit = mode == M_LIT;
-				v = load8(lit ? src + ip : dst + op - off, n, lit ? src_end : dst + cap);
+				v = load16(lit ? src + ip : dst + op - off, n, lit ? src_end : dst + cap);
 				if (lit)
 					ip += n;
 			}
 			// append the n low bytes of v (op + n <= cap was checked with the tag)
-			const uint32_t k = op & 7u, sh = 8u * k;
-			if (n < 8)
-				v &= (1ull << (8u * n)) - 1ull;
-			acc |= v << sh;
-			if (k + n >= 8) {
-				stg64(dst + (op & ~7u), acc);  // a complete word lies below op + n <= cap
-				acc = k ? v >> (64u - sh) : 0ull;
+			if (n < 16) {
+				const uint64_t m = ~0ull >> (8u * (8u - (n & 7u)) & 63u);  // low (n & 7) bytes; all ones for n & 7 == 0
+				if (n < 8) {
+					v.lo &= m;
+					v.hi = 0;
+				} else if (n > 8) {
+					v.hi &= m;
+				} else {
+					v.hi = 0;
+				}
+			}
+			const uint32_t k = op & 15u, s = k & 7u;
+			// v << 8 k as four words y0..y3 (k = 8 q + s)
+			const uint64_t t0 = v.lo << (8u * s);
+			const uint64_t t1 = (v.hi << (8u * s)) | ((v.lo >> 1) >> (63u - 8u * s));
+			const uint64_t t2 = (v.hi >> 1) >> (63u - 8u * s);
+			const bool q = k >= 8;
+			acc0 |= q ? 0ull : t0;
+			acc1 |= q ? t0 : t1;
+			if (k + n >= 16) {
+				stg128(dst + (op & ~15u), acc0, acc1);	// a complete vector lies below op + n <= cap
+				acc0 = q ? t1 : t2;
+				acc1 = q ? t2 : 0ull;
 			}
 			op += n;
 			rem -= n;
@@ -300,7 +320,7 @@ extern "C" int csb_launch_decompress_lane(const struct csb_decompress_args *a, c
 		return (int)ce;
 	p.counter = counter;
 	long ctas = ((long)a->n_blocks + kLaneThreads - 1) / kLaneThreads;
-	const long max_ctas = (long)di.sm_count * 6;  // persistent: lanes claim blocks until none is left
+	const long max_ctas = (long)di.sm_count * (a->ctas_per_sm > 0 ? a->ctas_per_sm : 5);  // persistent: lanes claim blocks until none is left
 	if (ctas > max_ctas)
 		ctas = max_ctas;
 	decompress_lane_kernel<<<(int)ctas, kLaneThreads, 0, s>>>(p);

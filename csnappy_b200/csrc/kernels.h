@@ -60,7 +60,7 @@ struct csb_decompress_args {
 /* all return 0 or a cudaError_t value (> 0) */
 int csb_launch_compress(const struct csb_compress_args *a, csb_stream_t s);
 int csb_launch_decompress(const struct csb_decompress_args *a, csb_stream_t s);
-int csb_launch_decompress_lane(const struct csb_decompress_args *a, csb_stream_t s); /* one lane per block; out and out_stride 8-byte aligned */
+int csb_launch_decompress_lane(const struct csb_decompress_args *a, csb_stream_t s); /* one lane per block; out and out_stride 16-byte aligned */
 int csb_launch_pack(const uint8_t *slots, uint64_t slot_stride, const uint32_t *len,
 		    uint32_t n_blocks, uint8_t *packed, uint64_t *off, csb_stream_t s);
 int csb_launch_pack_stored(const uint8_t *slots, uint64_t slot_stride, const uint32_t *len, uint32_t n_blocks,

@@ -10,7 +10,8 @@ from csnappy_b200 import synth
 
 L, wm, n, stage = (int(x) for x in sys.argv[1:5])
 reps = int(sys.argv[5]) if len(sys.argv) > 5 else 3
-d = synth.text_fragments(n, L, device="cuda") if L > 4096 else synth.mixed_pages(n, L, device="cuda", text="urls")
+only = sys.argv[6] if len(sys.argv) > 6 else ""
+d = synth.text_fragments(n, L, device="cuda") if L > 4096 else synth.mixed_pages(n, L, device="cuda", text="urls", only=only)
 ostride = cs.api.out_stride_for(L)
 out, olen = cs.batch_compress_fragments(d, L, n, wm)
 back = torch.empty(n * L, dtype=torch.uint8, device="cuda")
