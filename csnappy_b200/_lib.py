@@ -35,6 +35,11 @@ def _declare(L):
         "csnappy_bc_max_container_length": (u64, [u64, u32]),
         "csnappy_bc_compress_host": (i, [vp, u64, u32, vp, u64, C.POINTER(C.c_uint64), i]),
         "csnappy_bc_decompress_host": (i, [vp, u64, u32, vp, u64, C.POINTER(C.c_uint64), _u32p]),
+        "csnappy_batch_compress_workspace": (u64, [vp, u32, u32]),
+        "csnappy_batch_compress": (i, [vp, vp, u64, vp, u32, u32, vp, u64, vp, i, vp, u64, vp]),
+        "csnappy_bc_compress_host_multi": (i, [vp, u64, u32, vp, u64, C.POINTER(C.c_uint64), i, vp, i]),
+        "csnappy_bc_decompress_host_multi": (i, [vp, u64, u32, vp, u64, C.POINTER(C.c_uint64), _u32p, vp, i]),
+        "csnappy_b200_device_count": (i, []),
         "csnappy_b200_device_ok": (i, []),
         "csnappy_b200_last_error": (C.c_char_p, []),
         "csnappy_b200_kernel_launches": (u64, []),

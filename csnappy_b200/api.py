@@ -226,6 +226,58 @@ def bc_decompress_host(h_container, container_length: int, h_out, page_size: int
     return rc, olen.value, (bad.value if rc != 0 and bad.value != 0xFFFFFFFF else None)
 
 
+def bc_compress_host_multi(h_in, input_length: int, h_container, wm: int = 13, page_size: int = 4096, devices=None) -> int:
+    """bc_compress_host over several devices from this one process (devices: list of device indices, None = all
+    visible).  Same bytes as the single-device call."""
+    clen = C.c_uint64(0)
+    cap = h_container.nbytes if isinstance(h_container, np.ndarray) else h_container.numel() * h_container.element_size()
+    dev = (C.c_int * len(devices))(*devices) if devices else None
+    rc = lib().csnappy_bc_compress_host_multi(_host_ptr(h_in), input_length, page_size, _host_ptr(h_container), cap,
+                                              C.byref(clen), wm, dev, len(devices) if devices else 0)
+    _check(rc, "csnappy_bc_compress_host_multi")
+    return clen.value
+
+
+def bc_decompress_host_multi(h_container, container_length: int, h_out, page_size: int = 4096, devices=None):
+    """-> (rc, bytes produced, failed page or None) over several devices."""
+    olen = C.c_uint64(0)
+    bad = C.c_uint32(0xFFFFFFFF)
+    cap = h_out.nbytes if isinstance(h_out, np.ndarray) else h_out.numel() * h_out.element_size()
+    dev = (C.c_int * len(devices))(*devices) if devices else None
+    rc = lib().csnappy_bc_decompress_host_multi(_host_ptr(h_container), container_length, page_size, _host_ptr(h_out),
+                                                cap, C.byref(olen), C.byref(bad), dev, len(devices) if devices else 0)
+    if rc in (CSNAPPY_E_DEVICE, CSNAPPY_E_BAD_ARG):
+        _check(rc, "csnappy_bc_decompress_host_multi")
+    return rc, olen.value, (bad.value if rc != 0 and bad.value != 0xFFFFFFFF else None)
+
+
+def batch_compress(d_in, in_off, in_len, wm: int, *, out_stride: int | None = None):
+    """Device-resident batch of csnappy_compress (whole buffers, varint32 header + 32 KiB fragments each).
+    d_in: uint8 CUDA tensor; in_off / in_len: HOST sequences (offsets into d_in, lengths).
+    Returns (out uint8 [n * out_stride], out_len int32 [n], out_stride)."""
+    import torch
+
+    n = len(in_len)
+    h_len = np.ascontiguousarray(np.asarray(in_len, dtype=np.uint32))
+    h_off = np.ascontiguousarray(np.asarray(in_off, dtype=np.uint64))
+    longest = int(h_len.max()) if n else 0
+    if out_stride is None:
+        out_stride = (5 + longest + longest // 6 + 32 * max(1, -(-longest // FRAGMENT_MAX)) + 15) // 16 * 16
+    ws_bytes = lib().csnappy_batch_compress_workspace(h_len.ctypes.data, 0, n)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=d_in.device)
+    out = torch.empty(max(n * out_stride, 16), dtype=torch.uint8, device=d_in.device)
+    out_len = torch.empty(max(n, 1), dtype=torch.int32, device=d_in.device)
+    rc = lib().csnappy_batch_compress(_ptr(d_in), h_off.ctypes.data, 0, h_len.ctypes.data, 0, n, _ptr(out), out_stride,
+                                      _ptr(out_len), wm, _ptr(ws), ws_bytes, _stream_ptr())
+    _check(rc, "csnappy_batch_compress")
+    torch.cuda.current_stream().synchronize()  # the workspace dies with this frame
+    return out, out_len, out_stride
+
+
+def device_count() -> int:
+    return lib().csnappy_b200_device_count()
+
+
 def set_tuning(key: str, value: int):
     rc = lib().csnappy_b200_set_tuning(key.encode(), value)
     if rc != 0:

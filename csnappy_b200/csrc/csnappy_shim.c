@@ -7,15 +7,25 @@
  * argument checks, the varint32 framing (csnappy_compress.c:46-73,
  * csnappy_decompress.c:45-71), buffer staging and CUDA launches.  Every byte
  * of compressed or decompressed payload is produced by the sm_100a kernels in
- * compress_kernel.cu / decompress_kernel.cu.  There is no CPU fallback: without
- * a usable device the decompress calls return CSNAPPY_E_DEVICE and the compress
- * calls (no error channel in the reference ABI) abort loudly.
+ * compress_kernel.cu / decompress_kernel.cu / decompress_lane_kernel.cu /
+ * stream_kernel.cu.  There is no CPU fallback: without a usable device the
+ * decompress calls return CSNAPPY_E_DEVICE and the compress calls (no error
+ * channel in the reference ABI) abort loudly.
+ *
+ * Concurrency: like the reference (csnappy.h:46-72: re-entrant, callers may run
+ * concurrently on disjoint buffers) every host-pointer call takes a private
+ * staging CONTEXT (streams + device / pinned buffers) from a per-device pool, so
+ * concurrent callers overlap on the device instead of queueing behind one lock.
+ * The *_multi entry points shard one host buffer over several devices from ONE
+ * process: a worker thread and a context per device, no data-path collective; the
+ * only cross-device state is the running payload position of the container.
  */
 #include <cuda_runtime_api.h>
 #include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include "../../include/csnappy.h"
 #include "../../include/csnappy_batch.h"
@@ -24,6 +34,8 @@
 #define SLOT_STRIDE_32K 38272u /* csnappy_max_compressed_length(32768) = 38261, rounded up to 16 */
 #define HDR 16u		       /* device staging: [u32 out_len][i32 status][pad] then payload */
 #define SMALL_CALL 65536u      /* single calls up to this size take the one-synchronisation path */
+#define PIPE 4		       /* chunks in flight per device in the host-buffer pipelines */
+#define MAX_DEV 64
 
 static __thread char tls_err[256];
 
@@ -36,7 +48,7 @@ static int set_err(const char *what, int cuda_err)
 
 const char *csnappy_b200_last_error(void) { return tls_err; }
 
-int csnappy_b200_device_ok(void)
+int csnappy_b200_device_count(void)
 {
 	int n = 0;
 	cudaError_t e = cudaGetDeviceCount(&n);
@@ -45,13 +57,15 @@ int csnappy_b200_device_ok(void)
 		cudaGetLastError();
 		return 0;
 	}
-	return n > 0;
+	return n;
 }
+
+int csnappy_b200_device_ok(void) { return csnappy_b200_device_count() > 0; }
 
 uint64_t csnappy_b200_kernel_launches(void) { return csb_launch_count(); }
 
 /* ---- tuning knobs ------------------------------------------------------- */
-static int g_compress_lanes, g_decompress_lanes, g_ctas_per_sm, g_stage_input, g_smem_kb;
+static int g_compress_lanes, g_decompress_lanes, g_ctas_per_sm, g_stage_input, g_smem_kb, g_host_register, g_stream_min;
 
 int csnappy_b200_set_tuning(const char *key, int value)
 {
@@ -82,6 +96,16 @@ int csnappy_b200_set_tuning(const char *key, int value)
 		if (value < 0 || value > 8)
 			return CSNAPPY_E_BAD_ARG;
 		g_ctas_per_sm = value;
+		return 0;
+	}
+	if (!strcmp(key, "host_register")) { /* 1: page-lock the caller's buffers for the duration of a host-buffer call */
+		if (value < 0 || value > 1)
+			return CSNAPPY_E_BAD_ARG;
+		g_host_register = value;
+		return 0;
+	}
+	if (!strcmp(key, "stream_decode_min")) { /* single streams at least this long (bytes) use the parallel stream decoder; 0 = default, -1 = never */
+		g_stream_min = value;
 		return 0;
 	}
 	return CSNAPPY_E_BAD_ARG;
@@ -118,6 +142,22 @@ static uint32_t put_varint32(uint8_t *out, uint32_t v)
 	return k;
 }
 
+static void fill_compress_args(struct csb_compress_args *a)
+{
+	memset(a, 0, sizeof(*a));
+	a->lanes = g_compress_lanes;
+	a->ctas_per_sm = g_ctas_per_sm;
+}
+
+static void fill_decompress_args(struct csb_decompress_args *a)
+{
+	memset(a, 0, sizeof(*a));
+	a->lanes = g_decompress_lanes;
+	a->stage_input = g_stage_input;
+	a->smem_kb = g_smem_kb;
+	a->ctas_per_sm = g_ctas_per_sm;
+}
+
 /* ---- batched device-pointer entry points -------------------------------- */
 int csnappy_batch_compress_fragments(const void *d_in, const uint64_t *d_in_off, uint64_t in_stride,
 				     const uint32_t *d_in_len, uint32_t uniform_in_len, uint32_t n_blocks,
@@ -132,7 +172,7 @@ int csnappy_batch_compress_fragments(const void *d_in, const uint64_t *d_in_off,
 		return set_err("fragment longer than 32768 bytes", 0);
 	if (n_blocks && (!d_in || !d_out || !d_out_len))
 		return set_err("null buffer", 0);
-	memset(&a, 0, sizeof(a));
+	fill_compress_args(&a);
 	a.in = (const uint8_t *)d_in;
 	a.in_off = d_in_off;
 	a.in_stride = in_stride;
@@ -144,8 +184,6 @@ int csnappy_batch_compress_fragments(const void *d_in, const uint64_t *d_in_off,
 	a.out_len = d_out_len;
 	a.wm = workmem_bytes_power_of_two;
 	a.flags = flags;
-	a.lanes = g_compress_lanes;
-	a.ctas_per_sm = g_ctas_per_sm;
 	e = csb_launch_compress(&a, (csb_stream_t)stream);
 	return e ? set_err("compress launch", e) : 0;
 }
@@ -159,7 +197,7 @@ int csnappy_batch_decompress(const void *d_in, const uint64_t *d_in_off, uint64_
 	int e;
 	if (n_blocks && (!d_in || !d_in_len || !d_out_len || !d_status))
 		return set_err("null buffer", 0);
-	memset(&a, 0, sizeof(a));
+	fill_decompress_args(&a);
 	a.in = (const uint8_t *)d_in;
 	a.in_off = d_in_off;
 	a.in_stride = in_stride;
@@ -172,10 +210,6 @@ int csnappy_batch_decompress(const void *d_in, const uint64_t *d_in_off, uint64_
 	a.out_len = d_out_len;
 	a.status = d_status;
 	a.flags = flags;
-	a.lanes = g_decompress_lanes;
-	a.stage_input = g_stage_input;
-	a.smem_kb = g_smem_kb;
-	a.ctas_per_sm = g_ctas_per_sm;
 	e = csb_launch_decompress(&a, (csb_stream_t)stream);
 	return e ? set_err("decompress launch", e) : 0;
 }
@@ -191,32 +225,150 @@ int csnappy_batch_pack(const void *d_slots, uint64_t slot_stride, const uint32_t
 	return e ? set_err("pack launch", e) : 0;
 }
 
-/* ---- staging context for the host-pointer calls ------------------------- */
+/* ---- batched csnappy_compress: many whole buffers, each framed, in one call ------------------------------
+ * (csnappy_compress.c:621-656 per buffer: varint32, 32 KiB fragments, short-last-chunk table rule.)
+ * The fragment table is laid out on the host from the buffer lengths, so the lengths are needed there.
+ * Workspace (device): fragment slots | sizes | scan | fragment table | buffer table.                          */
+static uint64_t frags_of(uint32_t len) { return ((uint64_t)len + CSB_FRAGMENT_MAX - 1) / CSB_FRAGMENT_MAX; }
+
+static uint64_t al256(uint64_t x) { return (x + 255) & ~(uint64_t)255; }
+
+static uint64_t batch_compress_layout(uint64_t F, uint64_t n, uint64_t *o_len, uint64_t *o_off, uint64_t *o_foff,
+				      uint64_t *o_flen, uint64_t *o_fbuf, uint64_t *o_bfirst, uint64_t *o_blen)
+{
+	uint64_t p = al256(F * SLOT_STRIDE_32K);
+	*o_len = p;
+	p = al256(p + F * 4);
+	*o_off = p;
+	p = al256(p + (F + 1) * 8);
+	*o_foff = p;
+	p = al256(p + F * 8);
+	*o_flen = p;
+	p = al256(p + F * 4);
+	*o_fbuf = p;
+	p = al256(p + F * 4);
+	*o_bfirst = p;
+	p = al256(p + (n + 1) * 4);
+	*o_blen = p;
+	p = al256(p + n * 4);
+	return p + 256;
+}
+
+uint64_t csnappy_batch_compress_workspace(const uint32_t *h_in_len, uint32_t uniform_in_len, uint32_t n_buffers)
+{
+	uint64_t F = 0, a, b, c, d, e, f, g;
+	uint32_t i;
+	for (i = 0; i < n_buffers; i++)
+		F += frags_of(h_in_len ? h_in_len[i] : uniform_in_len);
+	return batch_compress_layout(F, n_buffers, &a, &b, &c, &d, &e, &f, &g);
+}
+
+int csnappy_batch_compress(const void *d_in, const uint64_t *h_in_off, uint64_t in_stride, const uint32_t *h_in_len,
+			   uint32_t uniform_in_len, uint32_t n_buffers, void *d_out, uint64_t out_stride,
+			   uint32_t *d_out_len, int workmem_bytes_power_of_two, void *d_workspace,
+			   uint64_t workspace_bytes, void *stream)
+{
+	uint64_t F = 0, o_len, o_off, o_foff, o_flen, o_fbuf, o_bfirst, o_blen, need, f = 0;
+	uint32_t i, max_len = 0;
+	uint8_t *ws = (uint8_t *)d_workspace, *tab = NULL;
+	struct csb_compress_args a;
+	cudaStream_t s = (cudaStream_t)stream;
+	int e;
+	if (workmem_bytes_power_of_two < 9 || workmem_bytes_power_of_two > 16)
+		return set_err("workmem_bytes_power_of_two outside 9..16", 0);
+	if (n_buffers == 0)
+		return 0;
+	if (!d_in || !d_out || !d_out_len || !d_workspace)
+		return set_err("null buffer", 0);
+	for (i = 0; i < n_buffers; i++) {
+		uint32_t n = h_in_len ? h_in_len[i] : uniform_in_len;
+		F += frags_of(n);
+		if (n > max_len)
+			max_len = n;
+	}
+	if (F > 0xffffffffull)
+		return set_err("more than 2^32 fragments", 0);
+	if (out_stride < 5ull + max_len + max_len / 6 + 32ull * (frags_of(max_len) ? frags_of(max_len) : 1))
+		return set_err("out_stride smaller than the worst case of its buffer (5 + n + n/6 + 32 per fragment)", 0);
+	need = batch_compress_layout(F, n_buffers, &o_len, &o_off, &o_foff, &o_flen, &o_fbuf, &o_bfirst, &o_blen);
+	if (workspace_bytes < need)
+		return set_err("workspace smaller than csnappy_batch_compress_workspace()", 0);
+	/* host image of the tables [o_foff, need): fragment offsets / lengths / owners, first fragment and length per buffer */
+	tab = (uint8_t *)malloc((size_t)(need - o_foff));
+	if (!tab)
+		return set_err("host table", (int)cudaErrorMemoryAllocation);
+	{
+		uint64_t *foff = (uint64_t *)tab;
+		uint32_t *flen = (uint32_t *)(tab + (o_flen - o_foff)), *fbuf = (uint32_t *)(tab + (o_fbuf - o_foff));
+		uint32_t *bfirst = (uint32_t *)(tab + (o_bfirst - o_foff)), *blen = (uint32_t *)(tab + (o_blen - o_foff));
+		for (i = 0; i < n_buffers; i++) {
+			uint32_t n = h_in_len ? h_in_len[i] : uniform_in_len, at = 0;
+			uint64_t base = h_in_off ? h_in_off[i] : (uint64_t)i * in_stride;
+			bfirst[i] = (uint32_t)f;
+			blen[i] = n;
+			while (at < n) {
+				uint32_t m = n - at < CSB_FRAGMENT_MAX ? n - at : CSB_FRAGMENT_MAX;
+				foff[f] = base + at;
+				flen[f] = m;
+				fbuf[f] = i;
+				f++;
+				at += m;
+			}
+		}
+		bfirst[n_buffers] = (uint32_t)f;
+	}
+	/* pageable source: the copy is staged before the call returns, the table can be freed right after */
+	e = (int)cudaMemcpyAsync(ws + o_foff, tab, (size_t)(need - o_foff), cudaMemcpyHostToDevice, s);
+	free(tab);
+	if (e)
+		return set_err("H2D fragment table", e);
+	if (F) {
+		fill_compress_args(&a);
+		a.in = (const uint8_t *)d_in;
+		a.in_off = (const uint64_t *)(ws + o_foff);
+		a.in_len = (const uint32_t *)(ws + o_flen);
+		a.n_blocks = (uint32_t)F;
+		a.out = ws;
+		a.out_stride = SLOT_STRIDE_32K;
+		a.out_len = (uint32_t *)(ws + o_len);
+		a.wm = workmem_bytes_power_of_two;
+		a.flags = CSNAPPY_BATCH_SHRINK_TABLE;
+		if ((e = csb_launch_compress(&a, (csb_stream_t)s)))
+			return set_err("compress launch", e);
+	}
+	if ((e = csb_launch_scan((const uint32_t *)(ws + o_len), (uint32_t)F, (uint64_t *)(ws + o_off), (csb_stream_t)s)))
+		return set_err("scan launch", e);
+	e = csb_launch_frame(ws, SLOT_STRIDE_32K, (const uint32_t *)(ws + o_len), (const uint64_t *)(ws + o_off),
+			     (const uint32_t *)(ws + o_fbuf), (const uint32_t *)(ws + o_bfirst), (const uint32_t *)(ws + o_blen),
+			     (uint32_t)F, n_buffers, (uint8_t *)d_out, out_stride, d_out_len, (csb_stream_t)s);
+	return e ? set_err("frame launch", e) : 0;
+}
+
+/* ---- staging contexts for the host-pointer calls ------------------------ */
 struct buf {
 	void *p;
 	size_t cap;
 };
 
-static struct {
-	pthread_mutex_t mu;
-	int ready;
-	cudaStream_t stream[3];
-	struct buf d_in, d_out, d_aux, d_pack; /* device */
-	struct buf h_pin;		       /* pinned host bounce buffer */
-	struct buf d_in2[3], d_out2[3], d_aux2[3], d_ctr2[3], d_ctr;
-} C = {.mu = PTHREAD_MUTEX_INITIALIZER};
+struct slot {
+	cudaStream_t s;
+	cudaEvent_t ev;
+	struct buf d_in, d_slots, d_len, d_clen, d_off, d_packed, d_out, d_res, d_ctr;
+	struct buf h_res; /* pinned: [u64 total] or [u32 out_len[n]][i32 status[n]] */
+	uint64_t first;
+	uint32_t n;
+};
 
-static int ctx_init(void)
-{
-	int i, e;
-	if (C.ready)
-		return 0;
-	for (i = 0; i < 3; i++)
-		if ((e = (int)cudaStreamCreateWithFlags(&C.stream[i], cudaStreamNonBlocking)))
-			return e;
-	C.ready = 1;
-	return 0;
-}
+struct ctx {
+	struct ctx *next;
+	int dev;
+	struct slot sl[PIPE];
+	struct buf h_pin;	/* pinned bounce buffer of the single small calls */
+	struct buf d_aux, d_aux2; /* stream decoder tables */
+};
+
+static pthread_mutex_t pool_mu = PTHREAD_MUTEX_INITIALIZER;
+static struct ctx *pool_free[MAX_DEV];
 
 static int grow_dev(struct buf *b, size_t need)
 {
@@ -228,8 +380,10 @@ static int grow_dev(struct buf *b, size_t need)
 	b->p = NULL;
 	b->cap = 0;
 	need = (need + (1u << 20)) & ~(size_t)((1u << 20) - 1);
-	if ((e = (int)cudaMalloc(&b->p, need)))
+	if ((e = (int)cudaMalloc(&b->p, need))) {
+		cudaGetLastError();
 		return e;
+	}
 	b->cap = need;
 	return 0;
 }
@@ -244,10 +398,99 @@ static int grow_pin(struct buf *b, size_t need)
 	b->p = NULL;
 	b->cap = 0;
 	need = (need + (1u << 16)) & ~(size_t)((1u << 16) - 1);
-	if ((e = (int)cudaMallocHost(&b->p, need)))
+	if ((e = (int)cudaMallocHost(&b->p, need))) {
+		cudaGetLastError();
 		return e;
+	}
 	b->cap = need;
 	return 0;
+}
+
+static void drop_dev(struct buf *b)
+{
+	if (b->p)
+		cudaFree(b->p);
+	b->p = NULL;
+	b->cap = 0;
+}
+
+/* a context of the CURRENT device: from the pool, or a new one */
+static int ctx_acquire(struct ctx **out)
+{
+	struct ctx *c = NULL;
+	int dev = 0, e, i;
+	if ((e = (int)cudaGetDevice(&dev)))
+		return e;
+	if (dev < 0 || dev >= MAX_DEV)
+		return (int)cudaErrorInvalidDevice;
+	pthread_mutex_lock(&pool_mu);
+	c = pool_free[dev];
+	if (c)
+		pool_free[dev] = c->next;
+	pthread_mutex_unlock(&pool_mu);
+	if (!c) {
+		c = (struct ctx *)calloc(1, sizeof(*c));
+		if (!c)
+			return (int)cudaErrorMemoryAllocation;
+		c->dev = dev;
+		for (i = 0; i < PIPE; i++) {
+			if ((e = (int)cudaStreamCreateWithFlags(&c->sl[i].s, cudaStreamNonBlocking)) ||
+			    (e = (int)cudaEventCreateWithFlags(&c->sl[i].ev, cudaEventDisableTiming))) {
+				free(c); /* (streams of a failed init leak; the process is in trouble anyway) */
+				return e;
+			}
+		}
+	}
+	c->next = NULL;
+	*out = c;
+	return 0;
+}
+
+static void ctx_release(struct ctx *c)
+{
+	if (!c)
+		return;
+	pthread_mutex_lock(&pool_mu);
+	c->next = pool_free[c->dev];
+	pool_free[c->dev] = c;
+	pthread_mutex_unlock(&pool_mu);
+}
+
+/* free the device buffers of every idle context of the current device (after an allocation failure) */
+static void pool_trim(void)
+{
+	struct ctx *c;
+	int dev = 0, i;
+	if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV)
+		return;
+	pthread_mutex_lock(&pool_mu);
+	for (c = pool_free[dev]; c; c = c->next) {
+		for (i = 0; i < PIPE; i++) {
+			struct slot *s = &c->sl[i];
+			drop_dev(&s->d_in);
+			drop_dev(&s->d_slots);
+			drop_dev(&s->d_len);
+			drop_dev(&s->d_clen);
+			drop_dev(&s->d_off);
+			drop_dev(&s->d_packed);
+			drop_dev(&s->d_out);
+			drop_dev(&s->d_res);
+		}
+		drop_dev(&c->d_aux);
+		drop_dev(&c->d_aux2);
+	}
+	pthread_mutex_unlock(&pool_mu);
+}
+
+/* grow with one retry after releasing what idle contexts hold (a transient shortage must not abort a compress call) */
+static int grow_dev_retry(struct buf *b, size_t need)
+{
+	int e = grow_dev(b, need);
+	if (e == (int)cudaErrorMemoryAllocation) {
+		pool_trim();
+		e = grow_dev(b, need);
+	}
+	return e;
 }
 
 #define TRY(what, expr)                          \
@@ -265,6 +508,280 @@ static void die_no_error_channel(const char *fn)
 	abort();
 }
 
+/* optional page-locking of caller memory for the duration of a call ("host_register" knob) */
+struct hostreg {
+	void *p;
+};
+static void hostreg_begin(struct hostreg *r, const void *p, size_t n)
+{
+	const size_t pg = (size_t)sysconf(_SC_PAGESIZE);
+	uintptr_t a = ((uintptr_t)p + pg - 1) & ~(uintptr_t)(pg - 1), b = ((uintptr_t)p + n) & ~(uintptr_t)(pg - 1);
+	r->p = NULL;
+	if (!g_host_register || !p || b <= a || b - a < (8u << 20))
+		return;
+	if (cudaHostRegister((void *)a, b - a, cudaHostRegisterPortable) == cudaSuccess)
+		r->p = (void *)a;
+	else
+		cudaGetLastError(); /* already pinned by the caller, or not registrable: copy from it as it is */
+}
+static void hostreg_end(struct hostreg *r)
+{
+	if (r->p)
+		cudaHostUnregister(r->p);
+	r->p = NULL;
+}
+
+/* ---- single small calls: one fragment / one small stream -------------------------------------------------- */
+
+/* one fragment (the per-page call of zram / block_compressor): pinned bounce buffers, the size travels in front of the
+ * slot, ONE stream synchronisation.  Returns bytes written to out or a negative error. */
+static int64_t compress_one(const uint8_t *in, uint32_t n, uint8_t *out, int wm, uint32_t kflags)
+{
+	int64_t rc = 0;
+	struct ctx *c = NULL;
+	struct slot *sl;
+	struct csb_compress_args a;
+	const size_t in_pad = ((size_t)n + 63) & ~(size_t)63, slot = HDR + csnappy_max_compressed_length(n);
+	uint8_t *pin;
+	uint32_t clen;
+	TRY("context", ctx_acquire(&c));
+	sl = &c->sl[0];
+	TRY("cudaMallocHost", grow_pin(&c->h_pin, in_pad + slot + 64));
+	TRY("cudaMalloc(in)", grow_dev_retry(&sl->d_in, (size_t)n + 64));
+	TRY("cudaMalloc(slots)", grow_dev_retry(&sl->d_slots, SLOT_STRIDE_32K + HDR));
+	TRY("cudaMalloc(ctr)", grow_dev_retry(&sl->d_ctr, 64));
+	pin = (uint8_t *)c->h_pin.p;
+	memcpy(pin, in, n);
+	TRY("H2D", cudaMemcpyAsync(sl->d_in.p, pin, n, cudaMemcpyHostToDevice, sl->s));
+	fill_compress_args(&a);
+	a.in = (const uint8_t *)sl->d_in.p;
+	a.in_stride = CSB_FRAGMENT_MAX;
+	a.uniform_len = n;
+	a.n_blocks = 1;
+	a.out = (uint8_t *)sl->d_slots.p + HDR;
+	a.out_stride = SLOT_STRIDE_32K;
+	a.out_len = (uint32_t *)sl->d_slots.p;
+	a.wm = wm;
+	a.flags = kflags;
+	a.counter = (uint32_t *)sl->d_ctr.p;
+	TRY("compress launch", csb_launch_compress(&a, (csb_stream_t)sl->s));
+	TRY("D2H", cudaMemcpyAsync(pin + in_pad, sl->d_slots.p, slot, cudaMemcpyDeviceToHost, sl->s));
+	TRY("sync", cudaStreamSynchronize(sl->s));
+	memcpy(&clen, pin + in_pad, 4);
+	memcpy(out, pin + in_pad + HDR, clen);
+	rc = (int64_t)clen;
+out:
+	ctx_release(c);
+	return rc;
+}
+
+/* ---- compress pipeline: pages / fragments of ONE host buffer through one or several devices ---------------
+ * Used by the block_compressor container writer (stored-block rule, size index) and by csnappy_compress on
+ * large buffers (32 KiB fragments, short-last-chunk table rule, no index).  The buffer is cut into chunks;
+ * chunk c goes to device c mod G.  Per chunk: H2D, compress kernel, size scan + pack on the device, then only
+ * the PACKED payload travels back, straight to its final position.  That position is the sum of the packed
+ * sizes of all earlier chunks: the one value that crosses devices, handed from chunk to chunk in order.     */
+struct cjob {
+	const uint8_t *in;
+	uint64_t in_len;
+	uint32_t page;
+	int wm;
+	uint32_t kflags;
+	int stored;	      /* block_compressor.c:316-318 */
+	uint8_t *index_out;   /* u32 per page, or NULL */
+	uint8_t *payload_out; /* payload byte 0 */
+	uint64_t nr, n_chunks;
+	uint32_t chunk;
+	int G;
+	const int *devs; /* NULL: the current device (G == 1) */
+	pthread_mutex_t mu;
+	pthread_cond_t cv;
+	uint64_t pos_chunk, pos; /* payload position of chunk pos_chunk */
+	int err;
+	char errtext[256];
+};
+
+struct cworker {
+	struct cjob *j;
+	int g;
+	pthread_t th;
+};
+
+static void cjob_fail(struct cjob *j, int rc)
+{
+	pthread_mutex_lock(&j->mu);
+	if (!j->err) {
+		j->err = rc;
+		memcpy(j->errtext, tls_err, sizeof(j->errtext));
+	}
+	pthread_cond_broadcast(&j->cv);
+	pthread_mutex_unlock(&j->mu);
+}
+
+static void *compress_worker(void *arg)
+{
+	struct cworker *w = (struct cworker *)arg;
+	struct cjob *j = w->j;
+	struct ctx *c = NULL;
+	const uint32_t out_stride = (csnappy_max_compressed_length(j->page) + 15u) & ~15u;
+	const uint64_t n_mine = (uint64_t)w->g < j->n_chunks ? (j->n_chunks - (uint64_t)w->g + (uint64_t)j->G - 1) / (uint64_t)j->G : 0;
+	uint64_t issued = 0, retired = 0;
+	int rc = 0, k;
+	if (j->devs)
+		TRY("cudaSetDevice", cudaSetDevice(j->devs[w->g]));
+	if (n_mine == 0)
+		return NULL;
+	TRY("context", ctx_acquire(&c));
+	for (k = 0; k < PIPE && (uint64_t)k < n_mine; k++) {
+		struct slot *b = &c->sl[k];
+		TRY("cudaMalloc(in)", grow_dev_retry(&b->d_in, (size_t)j->chunk * j->page + 64));
+		TRY("cudaMalloc(slots)", grow_dev_retry(&b->d_slots, (size_t)j->chunk * out_stride + 64));
+		TRY("cudaMalloc(len)", grow_dev_retry(&b->d_len, (size_t)j->chunk * 4 + 64));
+		TRY("cudaMalloc(clen)", grow_dev_retry(&b->d_clen, (size_t)j->chunk * 4 + 64));
+		TRY("cudaMalloc(off)", grow_dev_retry(&b->d_off, ((size_t)j->chunk + 1) * 8 + 64));
+		TRY("cudaMalloc(packed)", grow_dev_retry(&b->d_packed, (size_t)j->chunk * (j->stored ? j->page : out_stride) + 64));
+		TRY("cudaMallocHost(res)", grow_pin(&b->h_res, 64));
+		TRY("cudaMalloc(ctr)", grow_dev_retry(&b->d_ctr, 64));
+	}
+	while (retired < n_mine) {
+		if (j->err)
+			goto out; /* somebody else failed */
+		/* retire the oldest chunk once two younger ones are queued (or nothing is left to queue) */
+		if (retired < issued && (issued - retired > 2 || issued == n_mine)) {
+			struct slot *b = &c->sl[retired % PIPE];
+			const uint64_t gc = (uint64_t)w->g + retired * (uint64_t)j->G;
+			uint64_t total, pos;
+			TRY("event sync", cudaEventSynchronize(b->ev));
+			total = *(uint64_t *)b->h_res.p;
+			pthread_mutex_lock(&j->mu);
+			while (j->pos_chunk != gc && !j->err)
+				pthread_cond_wait(&j->cv, &j->mu);
+			pos = j->pos;
+			j->pos_chunk = gc + 1;
+			j->pos += total;
+			pthread_cond_broadcast(&j->cv);
+			pthread_mutex_unlock(&j->mu);
+			if (j->err)
+				goto out;
+			if (total)
+				TRY("D2H payload", cudaMemcpyAsync(j->payload_out + pos, b->d_packed.p, total, cudaMemcpyDeviceToHost, b->s));
+			retired++;
+			continue;
+		}
+		{
+			struct slot *b = &c->sl[issued % PIPE];
+			const uint64_t gc = (uint64_t)w->g + issued * (uint64_t)j->G;
+			const uint64_t first = gc * j->chunk, left_pages = j->nr - first, in_at = first * j->page;
+			const uint32_t nb = left_pages < j->chunk ? (uint32_t)left_pages : j->chunk;
+			const uint64_t in_bytes = j->in_len - in_at < (uint64_t)nb * j->page ? j->in_len - in_at : (uint64_t)nb * j->page;
+			struct csb_compress_args a;
+			TRY("H2D", cudaMemcpyAsync(b->d_in.p, j->in + in_at, in_bytes, cudaMemcpyHostToDevice, b->s));
+			fill_compress_args(&a);
+			a.in = (const uint8_t *)b->d_in.p;
+			a.in_stride = j->page;
+			a.uniform_len = j->page;
+			a.total_len = in_bytes;
+			a.n_blocks = nb;
+			a.out = (uint8_t *)b->d_slots.p;
+			a.out_stride = out_stride;
+			a.out_len = (uint32_t *)b->d_len.p;
+			a.wm = j->wm;
+			a.flags = j->kflags;
+			a.counter = (uint32_t *)b->d_ctr.p;
+			TRY("compress launch", csb_launch_compress(&a, (csb_stream_t)b->s));
+			if (j->stored) {
+				TRY("pack launch", csb_launch_pack_stored((const uint8_t *)b->d_slots.p, out_stride, (const uint32_t *)b->d_len.p, nb,
+									  (const uint8_t *)b->d_in.p, j->page, in_bytes, (uint32_t *)b->d_clen.p,
+									  (uint8_t *)b->d_packed.p, (uint64_t *)b->d_off.p, (csb_stream_t)b->s));
+			} else {
+				TRY("pack launch", csb_launch_pack((const uint8_t *)b->d_slots.p, out_stride, (const uint32_t *)b->d_len.p, nb,
+								   (uint8_t *)b->d_packed.p, (uint64_t *)b->d_off.p, (csb_stream_t)b->s));
+			}
+			TRY("D2H total", cudaMemcpyAsync(b->h_res.p, (uint64_t *)b->d_off.p + nb, 8, cudaMemcpyDeviceToHost, b->s));
+			if (j->index_out)
+				TRY("D2H index", cudaMemcpyAsync(j->index_out + 4 * first, j->stored ? b->d_clen.p : b->d_len.p, (size_t)nb * 4,
+								 cudaMemcpyDeviceToHost, b->s));
+			TRY("event record", cudaEventRecord(b->ev, b->s));
+			issued++;
+		}
+	}
+out:
+	if (c)
+		for (k = 0; k < PIPE; k++)
+			cudaStreamSynchronize(c->sl[k].s);
+	if (rc)
+		cjob_fail(j, rc);
+	ctx_release(c);
+	return NULL;
+}
+
+/* run the job on G devices (devs == NULL: inline on the current device); returns 0 or a negative error */
+static int run_cjob(struct cjob *j)
+{
+	struct cworker w[MAX_DEV];
+	int g;
+	pthread_mutex_init(&j->mu, NULL);
+	pthread_cond_init(&j->cv, NULL);
+	j->pos_chunk = 0;
+	j->pos = 0;
+	j->err = 0;
+	if (!j->devs) {
+		w[0].j = j;
+		w[0].g = 0;
+		compress_worker(&w[0]);
+	} else {
+		int started = 0;
+		for (g = 0; g < j->G; g++) {
+			w[g].j = j;
+			w[g].g = g;
+			if (pthread_create(&w[g].th, NULL, compress_worker, &w[g])) {
+				set_err("pthread_create", (int)cudaErrorUnknown);
+				cjob_fail(j, CSNAPPY_E_DEVICE);
+				break;
+			}
+			started++;
+		}
+		for (g = 0; g < started; g++)
+			pthread_join(w[g].th, NULL);
+	}
+	if (j->err)
+		memcpy(tls_err, j->errtext, sizeof(tls_err));
+	pthread_mutex_destroy(&j->mu);
+	pthread_cond_destroy(&j->cv);
+	return j->err;
+}
+
+static uint32_t chunk_units(uint32_t unit_bytes, uint64_t n_units, int G)
+{
+	/* ~32 MiB per chunk keeps PCIe busy and the kernels full; small inputs are still cut into a few chunks per device */
+	uint64_t units = (32ull << 20) / unit_bytes, per_dev = (n_units + (uint64_t)G - 1) / (uint64_t)G;
+	if (units > (per_dev + 3) / 4)
+		units = (per_dev + 3) / 4;
+	if (units < 256)
+		units = 256;
+	if (units > n_units)
+		units = n_units;
+	return (uint32_t)units;
+}
+
+/* device list of a *_multi call: devices NULL -> 0..n-1; n_devices 0 -> all visible */
+static int resolve_devices(const int *devices, int n_devices, int *list)
+{
+	int n = csnappy_b200_device_count(), i;
+	if (n <= 0)
+		return CSNAPPY_E_DEVICE;
+	if (n_devices < 0 || n_devices > MAX_DEV)
+		return set_err("n_devices", 0);
+	if (n_devices == 0)
+		n_devices = n;
+	for (i = 0; i < n_devices; i++) {
+		list[i] = devices ? devices[i] : i;
+		if (list[i] < 0 || list[i] >= n)
+			return set_err("device index outside the visible devices", 0);
+	}
+	return n_devices;
+}
+
 /*
  * Core of both compress entry points.  framed = 0: one fragment, no header.
  * framed = 1: varint32 + 32 KiB fragments with the short-chunk table rule.
@@ -272,91 +789,42 @@ static void die_no_error_channel(const char *fn)
  */
 static int64_t compress_host(const uint8_t *in, uint32_t n, uint8_t *out, int wm, int framed)
 {
-	int64_t rc = 0;
 	uint32_t hdr = framed ? put_varint32(out, n) : 0;
 	uint32_t n_frag = framed ? (uint32_t)(((uint64_t)n + CSB_FRAGMENT_MAX - 1) / CSB_FRAGMENT_MAX) : (n ? 1u : 0u);
-	struct csb_compress_args a;
-	cudaStream_t s;
-
 	if (wm < 9 || wm > 16)
 		return set_err("workmem_bytes_power_of_two outside 9..16", 0);
 	if (!framed && n > CSB_FRAGMENT_MAX)
 		return set_err("csnappy_compress_fragment: input longer than 32768 bytes", 0);
 	if (n_frag == 0)
 		return hdr;
-
-	pthread_mutex_lock(&C.mu);
-	TRY("stream create", ctx_init());
-	s = C.stream[0];
 	if (n_frag == 1) {
-		/* one fragment (the per-page call of zram / block_compressor): pinned bounce buffers, the size travels
-		 * in front of the slot, ONE stream synchronisation */
-		const size_t in_pad = ((size_t)n + 63) & ~(size_t)63, slot = HDR + csnappy_max_compressed_length(n);
-		uint8_t *pin;
-		uint32_t clen;
-		TRY("cudaMallocHost", grow_pin(&C.h_pin, in_pad + slot + 64));
-		TRY("cudaMalloc(in)", grow_dev(&C.d_in, (size_t)n + 64));
-		TRY("cudaMalloc(slots)", grow_dev(&C.d_out, SLOT_STRIDE_32K + HDR));
-		TRY("cudaMalloc(ctr)", grow_dev(&C.d_ctr, 64));
-		pin = (uint8_t *)C.h_pin.p;
-		memcpy(pin, in, n);
-		TRY("H2D", cudaMemcpyAsync(C.d_in.p, pin, n, cudaMemcpyHostToDevice, s));
-		memset(&a, 0, sizeof(a));
-		a.in = (const uint8_t *)C.d_in.p;
-		a.in_stride = CSB_FRAGMENT_MAX;
-		a.uniform_len = n;
-		a.n_blocks = 1;
-		a.out = (uint8_t *)C.d_out.p + HDR;
-		a.out_stride = SLOT_STRIDE_32K;
-		a.out_len = (uint32_t *)C.d_out.p;
-		a.wm = wm;
-		a.flags = framed ? CSNAPPY_BATCH_SHRINK_TABLE : 0;
-		a.lanes = g_compress_lanes;
-		a.ctas_per_sm = g_ctas_per_sm;
-		a.counter = (uint32_t *)C.d_ctr.p;
-		TRY("compress launch", csb_launch_compress(&a, (csb_stream_t)s));
-		TRY("D2H", cudaMemcpyAsync(pin + in_pad, C.d_out.p, slot, cudaMemcpyDeviceToHost, s));
-		TRY("sync", cudaStreamSynchronize(s));
-		memcpy(&clen, pin + in_pad, 4);
-		memcpy(out + hdr, pin + in_pad + HDR, clen);
-		rc = (int64_t)hdr + clen;
-		goto out;
+		int64_t r = compress_one(in, n, out + hdr, wm, framed ? CSNAPPY_BATCH_SHRINK_TABLE : 0);
+		return r < 0 ? r : (int64_t)hdr + r;
 	}
-	TRY("cudaMalloc(in)", grow_dev(&C.d_in, (size_t)n + 64));
-	TRY("cudaMalloc(slots)", grow_dev(&C.d_out, (size_t)n_frag * SLOT_STRIDE_32K));
-	TRY("cudaMalloc(aux)", grow_dev(&C.d_aux, HDR + (size_t)n_frag * 4 + ((size_t)n_frag + 1) * 8 + 64));
-	TRY("H2D", cudaMemcpyAsync(C.d_in.p, in, n, cudaMemcpyHostToDevice, s));
-
-	memset(&a, 0, sizeof(a));
-	a.in = (const uint8_t *)C.d_in.p;
-	a.in_stride = CSB_FRAGMENT_MAX;
-	a.uniform_len = n < CSB_FRAGMENT_MAX ? n : CSB_FRAGMENT_MAX;
-	a.total_len = n;
-	a.n_blocks = n_frag;
-	a.out = (uint8_t *)C.d_out.p;
-	a.out_stride = SLOT_STRIDE_32K;
-	a.out_len = (uint32_t *)C.d_aux.p;
-	a.wm = wm;
-	a.flags = framed ? CSNAPPY_BATCH_SHRINK_TABLE : 0;
-	a.lanes = g_compress_lanes;
-	a.ctas_per_sm = g_ctas_per_sm;
-	TRY("compress launch", csb_launch_compress(&a, (csb_stream_t)s));
-
 	{
-		uint64_t *d_off = (uint64_t *)((uint8_t *)C.d_aux.p + (((size_t)n_frag * 4 + 15) & ~(size_t)15));
-		uint64_t total = 0;
-		TRY("cudaMalloc(pack)", grow_dev(&C.d_pack, (size_t)n + (size_t)n / 6 + 32ull * n_frag + 64));
-		TRY("pack launch", csb_launch_pack((const uint8_t *)C.d_out.p, SLOT_STRIDE_32K, (const uint32_t *)C.d_aux.p,
-						   n_frag, (uint8_t *)C.d_pack.p, d_off, (csb_stream_t)s));
-		TRY("D2H total", cudaMemcpyAsync(&total, d_off + n_frag, 8, cudaMemcpyDeviceToHost, s));
-		TRY("sync", cudaStreamSynchronize(s));
-		TRY("D2H data", cudaMemcpyAsync(out + hdr, C.d_pack.p, total, cudaMemcpyDeviceToHost, s));
-		TRY("sync", cudaStreamSynchronize(s));
-		rc = (int64_t)hdr + (int64_t)total;
+		/* many fragments: chunks of fragments pipelined through the device (H2D of the next chunk overlaps the
+		 * kernels and the D2H of the previous ones), packed payload straight into `out` */
+		struct cjob j;
+		struct hostreg r1, r2;
+		int rc;
+		memset(&j, 0, sizeof(j));
+		j.in = in;
+		j.in_len = n;
+		j.page = CSB_FRAGMENT_MAX;
+		j.wm = wm;
+		j.kflags = CSNAPPY_BATCH_SHRINK_TABLE;
+		j.payload_out = out + hdr;
+		j.nr = n_frag;
+		j.G = 1;
+		j.chunk = chunk_units(CSB_FRAGMENT_MAX, n_frag, 1);
+		j.n_chunks = (j.nr + j.chunk - 1) / j.chunk;
+		hostreg_begin(&r1, in, n);
+		hostreg_begin(&r2, out, (size_t)n + n / 6);
+		rc = run_cjob(&j);
+		hostreg_end(&r1);
+		hostreg_end(&r2);
+		return rc ? rc : (int64_t)hdr + (int64_t)j.pos;
 	}
-out:
-	pthread_mutex_unlock(&C.mu);
-	return rc;
 }
 
 char *csnappy_compress_fragment(const char *input, const uint32_t input_length, char *output,
@@ -386,6 +854,8 @@ void csnappy_compress(const char *input, uint32_t input_length, char *compressed
 static int decompress_host(const uint8_t *src, uint32_t src_len, uint8_t *dst, uint32_t cap, uint32_t *produced)
 {
 	int rc = 0;
+	struct ctx *c = NULL;
+	struct slot *sl;
 	struct csb_decompress_args a;
 	cudaStream_t s;
 	struct {
@@ -394,42 +864,40 @@ static int decompress_host(const uint8_t *src, uint32_t src_len, uint8_t *dst, u
 	} res = {0, 0};
 	uint32_t *d_res;
 
-	pthread_mutex_lock(&C.mu);
-	TRY("stream create", ctx_init());
-	s = C.stream[0];
+	TRY("context", ctx_acquire(&c));
+	sl = &c->sl[0];
+	s = sl->s;
 	if (src_len <= SMALL_CALL && cap <= SMALL_CALL) {
 		/* one small block (the per-page call of zram / block_compressor): pinned bounce buffers, the input
 		 * length travels in front of the input and [out_len, status] in front of the output, ONE synchronisation */
 		const size_t in_bytes = HDR + src_len, in_pad = (in_bytes + 63) & ~(size_t)63, out_bytes = HDR + cap;
 		uint8_t *pin;
 		uint32_t *d_ihdr, *d_ohdr;
-		TRY("cudaMallocHost", grow_pin(&C.h_pin, in_pad + out_bytes + 64));
-		TRY("cudaMalloc(in)", grow_dev(&C.d_in, in_bytes + 64));
-		TRY("cudaMalloc(out)", grow_dev(&C.d_out, out_bytes + 64));
-		TRY("cudaMalloc(ctr)", grow_dev(&C.d_ctr, 64));
-		pin = (uint8_t *)C.h_pin.p;
+		TRY("cudaMallocHost", grow_pin(&c->h_pin, in_pad + out_bytes + 64));
+		TRY("cudaMalloc(in)", grow_dev_retry(&sl->d_in, in_bytes + 64));
+		TRY("cudaMalloc(out)", grow_dev_retry(&sl->d_out, out_bytes + 64));
+		TRY("cudaMalloc(ctr)", grow_dev_retry(&sl->d_ctr, 64));
+		pin = (uint8_t *)c->h_pin.p;
 		memset(pin, 0, HDR);
 		memcpy(pin, &src_len, 4);
 		memcpy(pin + HDR, src, src_len);
-		TRY("H2D", cudaMemcpyAsync(C.d_in.p, pin, in_bytes, cudaMemcpyHostToDevice, s));
-		d_ihdr = (uint32_t *)C.d_in.p;
-		d_ohdr = (uint32_t *)C.d_out.p;
-		memset(&a, 0, sizeof(a));
-		a.in = (const uint8_t *)C.d_in.p + HDR;
+		TRY("H2D", cudaMemcpyAsync(sl->d_in.p, pin, in_bytes, cudaMemcpyHostToDevice, s));
+		d_ihdr = (uint32_t *)sl->d_in.p;
+		d_ohdr = (uint32_t *)sl->d_out.p;
+		fill_decompress_args(&a);
+		if (a.stage_input == 4)
+			a.stage_input = 0; /* one block: never one lane */
+		a.in = (const uint8_t *)sl->d_in.p + HDR;
 		a.in_len = d_ihdr;
 		a.n_blocks = 1;
-		a.out = (uint8_t *)C.d_out.p + HDR;
+		a.out = (uint8_t *)sl->d_out.p + HDR;
 		a.uniform_cap = cap;
 		a.out_len = d_ohdr;
 		a.status = (int32_t *)(d_ohdr + 1);
 		a.max_in_len = src_len;
-		a.lanes = g_decompress_lanes;
-		a.stage_input = g_stage_input;
-		a.smem_kb = g_smem_kb;
-		a.ctas_per_sm = g_ctas_per_sm;
-		a.counter = (uint32_t *)C.d_ctr.p;
+		a.counter = (uint32_t *)sl->d_ctr.p;
 		TRY("decompress launch", csb_launch_decompress(&a, (csb_stream_t)s));
-		TRY("D2H", cudaMemcpyAsync(pin + in_pad, C.d_out.p, out_bytes, cudaMemcpyDeviceToHost, s));
+		TRY("D2H", cudaMemcpyAsync(pin + in_pad, sl->d_out.p, out_bytes, cudaMemcpyDeviceToHost, s));
 		TRY("sync", cudaStreamSynchronize(s));
 		memcpy(&res, pin + in_pad, 8);
 		rc = res.status;
@@ -439,41 +907,78 @@ static int decompress_host(const uint8_t *src, uint32_t src_len, uint8_t *dst, u
 		}
 		goto out;
 	}
-	TRY("cudaMalloc(in)", grow_dev(&C.d_in, (size_t)src_len + 64));
-	TRY("cudaMalloc(out)", grow_dev(&C.d_out, (size_t)cap + 64));
-	TRY("cudaMalloc(aux)", grow_dev(&C.d_aux, 64));
-	d_res = (uint32_t *)C.d_aux.p;
-	if (src_len)
-		TRY("H2D", cudaMemcpyAsync(C.d_in.p, src, src_len, cudaMemcpyHostToDevice, s));
-	TRY("H2D len", cudaMemcpyAsync(d_res + 2, &src_len, 4, cudaMemcpyHostToDevice, s));
-
-	memset(&a, 0, sizeof(a));
-	a.in = (const uint8_t *)C.d_in.p;
-	a.in_stride = 0;
-	a.in_len = d_res + 2;
-	a.n_blocks = 1;
-	a.out = (uint8_t *)C.d_out.p;
-	a.out_stride = 0;
-	a.uniform_cap = cap;
-	a.out_len = d_res;
-	a.status = (int32_t *)(d_res + 1);
-	a.max_in_len = src_len;
-	a.lanes = g_decompress_lanes;
-	a.stage_input = g_stage_input;
-	a.smem_kb = g_smem_kb;
-	a.ctas_per_sm = g_ctas_per_sm;
-	TRY("decompress launch", csb_launch_decompress(&a, (csb_stream_t)s));
-	TRY("D2H result", cudaMemcpyAsync(&res, d_res, 8, cudaMemcpyDeviceToHost, s));
-	TRY("sync", cudaStreamSynchronize(s));
-	rc = res.status;
-	if (rc == 0) {
-		if (res.out_len)
-			TRY("D2H data", cudaMemcpyAsync(dst, C.d_out.p, res.out_len, cudaMemcpyDeviceToHost, s));
-		TRY("sync", cudaStreamSynchronize(s));
-		*produced = res.out_len;
+	/* one long stream */
+	{
+		struct hostreg r1, r2;
+		const int use_stream = g_stream_min >= 0 && src_len >= (uint32_t)(g_stream_min ? g_stream_min : 16384);
+		TRY("cudaMalloc(in)", grow_dev_retry(&sl->d_in, (size_t)src_len + 64));
+		TRY("cudaMalloc(out)", grow_dev_retry(&sl->d_out, (size_t)cap + 64));
+		TRY("cudaMalloc(res)", grow_dev_retry(&sl->d_res, 64));
+		TRY("cudaMalloc(ctr)", grow_dev_retry(&sl->d_ctr, 64));
+		d_res = (uint32_t *)sl->d_res.p;
+		hostreg_begin(&r1, src, src_len);
+		hostreg_begin(&r2, dst, cap);
+		rc = 0;
+		do {
+			int e;
+			if (src_len && (e = (int)cudaMemcpyAsync(sl->d_in.p, src, src_len, cudaMemcpyHostToDevice, s))) {
+				rc = set_err("H2D", e);
+				break;
+			}
+			e = 1;
+			if (use_stream) {
+				/* parallel single-stream decoder (stream_kernel.cu); its tables: 8 bytes per input byte + 4 per output byte.
+				 * If they cannot be had, the serial warp-per-stream path below still decodes the stream. */
+				const size_t t1 = csb_stream_aux_bytes(src_len, cap, 0), t2 = csb_stream_aux_bytes(src_len, cap, 1);
+				if (!grow_dev(&c->d_aux, t1) && !grow_dev(&c->d_aux2, t2))
+					e = csb_launch_decompress_stream((const uint8_t *)sl->d_in.p, src_len, (uint8_t *)sl->d_out.p, cap, d_res,
+									 (int32_t *)(d_res + 1), c->d_aux.p, c->d_aux2.p, (csb_stream_t)s);
+				if (e > 1) {
+					rc = set_err("stream decoder launch", e);
+					break;
+				}
+			}
+			if (e == 1) {
+				if ((e = (int)cudaMemcpyAsync(d_res + 2, &src_len, 4, cudaMemcpyHostToDevice, s))) {
+					rc = set_err("H2D len", e);
+					break;
+				}
+				fill_decompress_args(&a);
+				if (a.stage_input == 4)
+					a.stage_input = 0;
+				a.in = (const uint8_t *)sl->d_in.p;
+				a.in_len = d_res + 2;
+				a.n_blocks = 1;
+				a.out = (uint8_t *)sl->d_out.p;
+				a.uniform_cap = cap;
+				a.out_len = d_res;
+				a.status = (int32_t *)(d_res + 1);
+				a.max_in_len = src_len;
+				a.counter = (uint32_t *)sl->d_ctr.p;
+				if ((e = csb_launch_decompress(&a, (csb_stream_t)s))) {
+					rc = set_err("decompress launch", e);
+					break;
+				}
+			}
+			if ((e = (int)cudaMemcpyAsync(&res, d_res, 8, cudaMemcpyDeviceToHost, s)) || (e = (int)cudaStreamSynchronize(s))) {
+				rc = set_err("D2H result", e);
+				break;
+			}
+			rc = res.status;
+			if (rc == 0) {
+				if (res.out_len && ((e = (int)cudaMemcpyAsync(dst, sl->d_out.p, res.out_len, cudaMemcpyDeviceToHost, s)) ||
+						    (e = (int)cudaStreamSynchronize(s)))) {
+					rc = set_err("D2H data", e);
+					break;
+				}
+				*produced = res.out_len;
+			}
+		} while (0);
+		hostreg_end(&r1);
+		hostreg_end(&r2);
 	}
 out:
-	pthread_mutex_unlock(&C.mu);
+	ctx_release(c);
 	return rc;
 }
 
@@ -497,9 +1002,7 @@ int csnappy_decompress(const char *src, uint32_t src_len, char *dst, uint32_t ds
 	return decompress_host((const uint8_t *)src + n, src_len - (uint32_t)n, (uint8_t *)dst, olen, &produced);
 }
 
-/* ---- host-buffer batches: chunked, three streams, H2D / kernel / D2H overlap ---- */
-#define NPIPE 3
-
+/* ---- host-buffer batches of strided slots: chunked, H2D / kernel / D2H overlap ---- */
 static size_t pick_chunk_blocks(uint64_t in_stride, uint64_t out_stride, uint32_t n_blocks)
 {
 	/* ~32 MiB of the larger side per chunk keeps PCIe busy and the kernels full */
@@ -518,6 +1021,7 @@ int csnappy_batch_compress_fragments_host(const void *h_in, uint64_t in_stride, 
 {
 	int rc = 0, k;
 	size_t chunk, done;
+	struct ctx *c = NULL;
 	if (workmem_bytes_power_of_two < 9 || workmem_bytes_power_of_two > 16)
 		return set_err("workmem_bytes_power_of_two outside 9..16", 0);
 	if (uniform_in_len > CSB_FRAGMENT_MAX || in_stride < uniform_in_len ||
@@ -528,46 +1032,43 @@ int csnappy_batch_compress_fragments_host(const void *h_in, uint64_t in_stride, 
 	if (!h_in || !h_out || !h_out_len)
 		return set_err("null buffer", 0);
 
-	pthread_mutex_lock(&C.mu);
-	TRY("stream create", ctx_init());
+	TRY("context", ctx_acquire(&c));
 	chunk = pick_chunk_blocks(in_stride, out_stride, n_blocks);
-	for (k = 0; k < NPIPE; k++) {
-		TRY("cudaMalloc(in)", grow_dev(&C.d_in2[k], chunk * in_stride + 64));
-		TRY("cudaMalloc(out)", grow_dev(&C.d_out2[k], chunk * out_stride + 64));
-		TRY("cudaMalloc(len)", grow_dev(&C.d_aux2[k], chunk * 4 + 64));
-		TRY("cudaMalloc(ctr)", grow_dev(&C.d_ctr2[k], 64));
+	for (k = 0; k < PIPE; k++) {
+		TRY("cudaMalloc(in)", grow_dev_retry(&c->sl[k].d_in, chunk * in_stride + 64));
+		TRY("cudaMalloc(out)", grow_dev_retry(&c->sl[k].d_slots, chunk * out_stride + 64));
+		TRY("cudaMalloc(len)", grow_dev_retry(&c->sl[k].d_len, chunk * 4 + 64));
+		TRY("cudaMalloc(ctr)", grow_dev_retry(&c->sl[k].d_ctr, 64));
 	}
-	for (done = 0, k = 0; done < n_blocks; done += chunk, k = (k + 1) % NPIPE) {
+	for (done = 0, k = 0; done < n_blocks; done += chunk, k = (k + 1) % PIPE) {
 		size_t nb = n_blocks - done < chunk ? n_blocks - done : chunk;
-		cudaStream_t s = C.stream[k];
+		struct slot *b = &c->sl[k];
 		struct csb_compress_args a;
-		TRY("H2D", cudaMemcpyAsync(C.d_in2[k].p, (const uint8_t *)h_in + done * in_stride, nb * in_stride,
-					   cudaMemcpyHostToDevice, s));
-		memset(&a, 0, sizeof(a));
-		a.in = (const uint8_t *)C.d_in2[k].p;
+		TRY("H2D", cudaMemcpyAsync(b->d_in.p, (const uint8_t *)h_in + done * in_stride, nb * in_stride,
+					   cudaMemcpyHostToDevice, b->s));
+		fill_compress_args(&a);
+		a.in = (const uint8_t *)b->d_in.p;
 		a.in_stride = in_stride;
 		a.uniform_len = uniform_in_len;
 		a.n_blocks = (uint32_t)nb;
-		a.out = (uint8_t *)C.d_out2[k].p;
+		a.out = (uint8_t *)b->d_slots.p;
 		a.out_stride = out_stride;
-		a.out_len = (uint32_t *)C.d_aux2[k].p;
+		a.out_len = (uint32_t *)b->d_len.p;
 		a.wm = workmem_bytes_power_of_two;
-		a.lanes = g_compress_lanes;
-		a.ctas_per_sm = g_ctas_per_sm;
-		a.counter = (uint32_t *)C.d_ctr2[k].p;
-		TRY("compress launch", csb_launch_compress(&a, (csb_stream_t)s));
-		TRY("D2H data", cudaMemcpyAsync((uint8_t *)h_out + done * out_stride, C.d_out2[k].p, nb * out_stride,
-						cudaMemcpyDeviceToHost, s));
-		TRY("D2H len", cudaMemcpyAsync(h_out_len + done, C.d_aux2[k].p, nb * 4, cudaMemcpyDeviceToHost, s));
+		a.counter = (uint32_t *)b->d_ctr.p;
+		TRY("compress launch", csb_launch_compress(&a, (csb_stream_t)b->s));
+		TRY("D2H data", cudaMemcpyAsync((uint8_t *)h_out + done * out_stride, b->d_slots.p, nb * out_stride,
+						cudaMemcpyDeviceToHost, b->s));
+		TRY("D2H len", cudaMemcpyAsync(h_out_len + done, b->d_len.p, nb * 4, cudaMemcpyDeviceToHost, b->s));
 	}
-	for (k = 0; k < NPIPE; k++)
-		TRY("sync", cudaStreamSynchronize(C.stream[k]));
 out:
-	if (rc)
-		for (k = 0; k < NPIPE; k++)
-			if (C.ready)
-				cudaStreamSynchronize(C.stream[k]);
-	pthread_mutex_unlock(&C.mu);
+	if (c)
+		for (k = 0; k < PIPE; k++) {
+			int e = (int)cudaStreamSynchronize(c->sl[k].s);
+			if (e && !rc)
+				rc = set_err("sync", e);
+		}
+	ctx_release(c);
 	return rc;
 }
 
@@ -577,6 +1078,7 @@ int csnappy_batch_decompress_host(const void *h_in, uint64_t in_stride, const ui
 {
 	int rc = 0, k;
 	size_t chunk, done;
+	struct ctx *c = NULL;
 	if (out_stride < uniform_out_cap)
 		return set_err("bad block geometry", 0);
 	if (n_blocks == 0)
@@ -592,54 +1094,49 @@ int csnappy_batch_decompress_host(const void *h_in, uint64_t in_stride, const ui
 				return set_err("h_in_len[i] larger than in_stride", 0);
 	}
 
-	pthread_mutex_lock(&C.mu);
-	TRY("stream create", ctx_init());
+	TRY("context", ctx_acquire(&c));
 	chunk = pick_chunk_blocks(in_stride, out_stride, n_blocks);
-	for (k = 0; k < NPIPE; k++) {
-		TRY("cudaMalloc(in)", grow_dev(&C.d_in2[k], chunk * in_stride + 64));
-		TRY("cudaMalloc(out)", grow_dev(&C.d_out2[k], chunk * out_stride + 64));
-		TRY("cudaMalloc(aux)", grow_dev(&C.d_aux2[k], chunk * 12 + 64));
-		TRY("cudaMalloc(ctr)", grow_dev(&C.d_ctr2[k], 64));
+	for (k = 0; k < PIPE; k++) {
+		TRY("cudaMalloc(in)", grow_dev_retry(&c->sl[k].d_in, chunk * in_stride + 64));
+		TRY("cudaMalloc(out)", grow_dev_retry(&c->sl[k].d_out, chunk * out_stride + 64));
+		TRY("cudaMalloc(aux)", grow_dev_retry(&c->sl[k].d_res, chunk * 12 + 64));
+		TRY("cudaMalloc(ctr)", grow_dev_retry(&c->sl[k].d_ctr, 64));
 	}
-	for (done = 0, k = 0; done < n_blocks; done += chunk, k = (k + 1) % NPIPE) {
+	for (done = 0, k = 0; done < n_blocks; done += chunk, k = (k + 1) % PIPE) {
 		size_t nb = n_blocks - done < chunk ? n_blocks - done : chunk;
-		cudaStream_t s = C.stream[k];
-		uint32_t *d_ilen = (uint32_t *)C.d_aux2[k].p, *d_olen = d_ilen + chunk;
+		struct slot *b = &c->sl[k];
+		uint32_t *d_ilen = (uint32_t *)b->d_res.p, *d_olen = d_ilen + chunk;
 		int32_t *d_st = (int32_t *)(d_olen + chunk);
 		struct csb_decompress_args a;
-		TRY("H2D", cudaMemcpyAsync(C.d_in2[k].p, (const uint8_t *)h_in + done * in_stride, nb * in_stride,
-					   cudaMemcpyHostToDevice, s));
-		TRY("H2D len", cudaMemcpyAsync(d_ilen, h_in_len + done, nb * 4, cudaMemcpyHostToDevice, s));
-		memset(&a, 0, sizeof(a));
-		a.in = (const uint8_t *)C.d_in2[k].p;
+		TRY("H2D", cudaMemcpyAsync(b->d_in.p, (const uint8_t *)h_in + done * in_stride, nb * in_stride,
+					   cudaMemcpyHostToDevice, b->s));
+		TRY("H2D len", cudaMemcpyAsync(d_ilen, h_in_len + done, nb * 4, cudaMemcpyHostToDevice, b->s));
+		fill_decompress_args(&a);
+		a.in = (const uint8_t *)b->d_in.p;
 		a.in_stride = in_stride;
 		a.in_len = d_ilen;
 		a.n_blocks = (uint32_t)nb;
-		a.out = (uint8_t *)C.d_out2[k].p;
+		a.out = (uint8_t *)b->d_out.p;
 		a.out_stride = out_stride;
 		a.uniform_cap = uniform_out_cap;
 		a.out_len = d_olen;
 		a.status = d_st;
 		a.flags = flags;
-		a.lanes = g_decompress_lanes;
-		a.stage_input = g_stage_input;
-		a.smem_kb = g_smem_kb;
-		a.ctas_per_sm = g_ctas_per_sm;
-		a.counter = (uint32_t *)C.d_ctr2[k].p;
-		TRY("decompress launch", csb_launch_decompress(&a, (csb_stream_t)s));
-		TRY("D2H data", cudaMemcpyAsync((uint8_t *)h_out + done * out_stride, C.d_out2[k].p, nb * out_stride,
-						cudaMemcpyDeviceToHost, s));
-		TRY("D2H len", cudaMemcpyAsync(h_out_len + done, d_olen, nb * 4, cudaMemcpyDeviceToHost, s));
-		TRY("D2H status", cudaMemcpyAsync(h_status + done, d_st, nb * 4, cudaMemcpyDeviceToHost, s));
+		a.counter = (uint32_t *)b->d_ctr.p;
+		TRY("decompress launch", csb_launch_decompress(&a, (csb_stream_t)b->s));
+		TRY("D2H data", cudaMemcpyAsync((uint8_t *)h_out + done * out_stride, b->d_out.p, nb * out_stride,
+						cudaMemcpyDeviceToHost, b->s));
+		TRY("D2H len", cudaMemcpyAsync(h_out_len + done, d_olen, nb * 4, cudaMemcpyDeviceToHost, b->s));
+		TRY("D2H status", cudaMemcpyAsync(h_status + done, d_st, nb * 4, cudaMemcpyDeviceToHost, b->s));
 	}
-	for (k = 0; k < NPIPE; k++)
-		TRY("sync", cudaStreamSynchronize(C.stream[k]));
 out:
-	if (rc)
-		for (k = 0; k < NPIPE; k++)
-			if (C.ready)
-				cudaStreamSynchronize(C.stream[k]);
-	pthread_mutex_unlock(&C.mu);
+	if (c)
+		for (k = 0; k < PIPE; k++) {
+			int e = (int)cudaStreamSynchronize(c->sl[k].s);
+			if (e && !rc)
+				rc = set_err("sync", e);
+		}
+	ctx_release(c);
 	return rc;
 }
 
@@ -649,63 +1146,24 @@ out:
  * payload_i is csnappy_compress_fragment(page_i, wm) or, when that is not smaller than the
  * page, the page itself with clen_i = its length (:316-318); the reader treats
  * clen_i == page_size as stored (:378).  Pages are compressed, size-scanned and packed on the
- * device chunk by chunk; four chunks are in flight so that H2D, kernels and D2H overlap, and
- * only COMPRESSED bytes cross the bus on the compressed side.
+ * device chunk by chunk (compress pipeline above); only COMPRESSED bytes cross the bus on the
+ * compressed side.
  */
-#define BC_PIPE 4
-
-struct bc_slot {
-	cudaStream_t s;
-	cudaEvent_t ev;
-	struct buf d_in, d_slots, d_len, d_clen, d_off, d_packed, d_out, d_res, d_ctr;
-	struct buf h_res; /* pinned: [u64 total] or [u32 out_len[n]][i32 status[n]] */
-	int busy;
-	uint64_t first;
-	uint32_t n;
-};
-static struct bc_slot BC[BC_PIPE];
-static int bc_ready;
-
-static int bc_init(void)
-{
-	int i, e;
-	if (bc_ready)
-		return 0;
-	for (i = 0; i < BC_PIPE; i++) {
-		if ((e = (int)cudaStreamCreateWithFlags(&BC[i].s, cudaStreamNonBlocking)))
-			return e;
-		if ((e = (int)cudaEventCreateWithFlags(&BC[i].ev, cudaEventDisableTiming)))
-			return e;
-	}
-	bc_ready = 1;
-	return 0;
-}
-
-static uint32_t bc_chunk_pages(uint32_t page_size, uint64_t nr_pages)
-{
-	uint64_t pages = (32ull << 20) / page_size;
-	if (pages < 256)
-		pages = 256;
-	if (pages > nr_pages)
-		pages = nr_pages;
-	return (uint32_t)pages;
-}
-
 uint64_t csnappy_bc_max_container_length(uint64_t input_length, uint32_t page_size)
 {
 	uint64_t nr = page_size ? (input_length + page_size - 1) / page_size : 0;
 	return 4 + 4 * nr + input_length;
 }
 
-int csnappy_bc_compress_host(const void *h_in, uint64_t input_length, uint32_t page_size, void *h_container,
-			     uint64_t container_capacity, uint64_t *container_length,
-			     int workmem_bytes_power_of_two)
+static int bc_compress(const void *h_in, uint64_t input_length, uint32_t page_size, void *h_container,
+		       uint64_t container_capacity, uint64_t *container_length, int wm, const int *devs, int G)
 {
-	int rc = 0, k;
-	uint64_t nr, done, payload_pos, retire_next = 0, issued = 0;
-	uint32_t chunk, out_stride;
+	uint64_t nr;
 	uint8_t *cont = (uint8_t *)h_container;
-	if (workmem_bytes_power_of_two < 9 || workmem_bytes_power_of_two > 16)
+	struct cjob j;
+	struct hostreg r1, r2;
+	int rc;
+	if (wm < 9 || wm > 16)
 		return set_err("workmem_bytes_power_of_two outside 9..16", 0);
 	if (page_size == 0 || page_size > CSB_FRAGMENT_MAX)
 		return set_err("page_size outside 1..32768", 0);
@@ -719,90 +1177,194 @@ int csnappy_bc_compress_host(const void *h_in, uint64_t input_length, uint32_t p
 		uint32_t nr32 = (uint32_t)nr;
 		memcpy(cont, &nr32, 4);
 	}
-	payload_pos = 4 + 4 * nr;
-	*container_length = payload_pos;
+	*container_length = 4 + 4 * nr;
 	if (nr == 0)
 		return 0;
-	chunk = bc_chunk_pages(page_size, nr);
-	out_stride = (csnappy_max_compressed_length(page_size) + 15u) & ~15u;
+	memset(&j, 0, sizeof(j));
+	j.in = (const uint8_t *)h_in;
+	j.in_len = input_length;
+	j.page = page_size;
+	j.wm = wm;
+	j.stored = 1;
+	j.index_out = cont + 4;
+	j.payload_out = cont + 4 + 4 * nr;
+	j.nr = nr;
+	j.G = G;
+	j.devs = devs;
+	j.chunk = chunk_units(page_size, nr, G);
+	j.n_chunks = (nr + j.chunk - 1) / j.chunk;
+	hostreg_begin(&r1, h_in, input_length);
+	hostreg_begin(&r2, h_container, container_capacity);
+	rc = run_cjob(&j);
+	hostreg_end(&r1);
+	hostreg_end(&r2);
+	if (rc)
+		return rc;
+	*container_length = 4 + 4 * nr + j.pos;
+	return 0;
+}
 
-	pthread_mutex_lock(&C.mu);
-	TRY("stream create", bc_init());
-	for (k = 0; k < BC_PIPE; k++) {
-		struct bc_slot *b = &BC[k];
-		TRY("cudaMalloc(in)", grow_dev(&b->d_in, (size_t)chunk * page_size + 64));
-		TRY("cudaMalloc(slots)", grow_dev(&b->d_slots, (size_t)chunk * out_stride + 64));
-		TRY("cudaMalloc(len)", grow_dev(&b->d_len, (size_t)chunk * 4 + 64));
-		TRY("cudaMalloc(clen)", grow_dev(&b->d_clen, (size_t)chunk * 4 + 64));
-		TRY("cudaMalloc(off)", grow_dev(&b->d_off, ((size_t)chunk + 1) * 8 + 64));
-		TRY("cudaMalloc(packed)", grow_dev(&b->d_packed, (size_t)chunk * page_size + 64));
-		TRY("cudaMallocHost(res)", grow_pin(&b->h_res, 64));
-		TRY("cudaMalloc(ctr)", grow_dev(&b->d_ctr, 64));
-		b->busy = 0;
+int csnappy_bc_compress_host(const void *h_in, uint64_t input_length, uint32_t page_size, void *h_container,
+			     uint64_t container_capacity, uint64_t *container_length,
+			     int workmem_bytes_power_of_two)
+{
+	return bc_compress(h_in, input_length, page_size, h_container, container_capacity, container_length,
+			   workmem_bytes_power_of_two, NULL, 1);
+}
+
+int csnappy_bc_compress_host_multi(const void *h_in, uint64_t input_length, uint32_t page_size, void *h_container,
+				   uint64_t container_capacity, uint64_t *container_length,
+				   int workmem_bytes_power_of_two, const int *devices, int n_devices)
+{
+	int list[MAX_DEV], G = resolve_devices(devices, n_devices, list);
+	if (G < 0)
+		return G;
+	return bc_compress(h_in, input_length, page_size, h_container, container_capacity, container_length,
+			   workmem_bytes_power_of_two, list, G);
+}
+
+/* ---- container reader: chunks of pages, chunk c on device c mod G; positions come from the index ---------- */
+struct djob {
+	const uint8_t *cont;
+	const uint8_t *idx; /* u32 per page (any alignment) */
+	uint32_t page, chunk;
+	uint8_t *out;
+	uint64_t nr; /* pages to decode (up to the first malformed index entry) */
+	uint64_t n_chunks;
+	const uint64_t *chunk_at;     /* container offset of each chunk's first payload byte (n_chunks + 1) */
+	const uint32_t *chunk_longest; /* longest compressed page of each chunk */
+	int G;
+	const int *devs;
+	pthread_mutex_t mu;
+	int first_err;
+	uint64_t err_page, produced;
+	int err;
+	char errtext[256];
+};
+
+struct dworker {
+	struct djob *j;
+	int g;
+	pthread_t th;
+};
+
+static void djob_fail(struct djob *j, int rc)
+{
+	pthread_mutex_lock(&j->mu);
+	if (!j->err) {
+		j->err = rc;
+		memcpy(j->errtext, tls_err, sizeof(j->errtext));
 	}
-	for (done = 0; done < nr || retire_next < issued;) {
-		/* retire the oldest chunk once two younger ones are queued (or nothing is left to queue) */
-		if (retire_next < issued && (issued - retire_next > 2 || done >= nr)) {
-			struct bc_slot *b = &BC[retire_next % BC_PIPE];
-			uint64_t total;
-			TRY("event sync", cudaEventSynchronize(b->ev));
-			total = *(uint64_t *)b->h_res.p;
-			TRY("D2H payload", cudaMemcpyAsync(cont + payload_pos, b->d_packed.p, total, cudaMemcpyDeviceToHost, b->s));
-			payload_pos += total;
-			retire_next++;
+	pthread_mutex_unlock(&j->mu);
+}
+
+static void *decompress_worker(void *arg)
+{
+	struct dworker *w = (struct dworker *)arg;
+	struct djob *j = w->j;
+	struct ctx *c = NULL;
+	const uint32_t max_clen = csnappy_max_compressed_length(j->page);
+	const uint64_t n_mine = (uint64_t)w->g < j->n_chunks ? (j->n_chunks - (uint64_t)w->g + (uint64_t)j->G - 1) / (uint64_t)j->G : 0;
+	uint64_t issued = 0, retired = 0;
+	int rc = 0, k;
+	if (j->devs)
+		TRY("cudaSetDevice", cudaSetDevice(j->devs[w->g]));
+	if (n_mine == 0)
+		return NULL;
+	TRY("context", ctx_acquire(&c));
+	for (k = 0; k < PIPE && (uint64_t)k < n_mine; k++) {
+		struct slot *b = &c->sl[k];
+		TRY("cudaMalloc(packed)", grow_dev_retry(&b->d_packed, (size_t)j->chunk * max_clen + 64));
+		TRY("cudaMalloc(clen)", grow_dev_retry(&b->d_clen, (size_t)j->chunk * 4 + 64));
+		TRY("cudaMalloc(off)", grow_dev_retry(&b->d_off, ((size_t)j->chunk + 1) * 8 + 64));
+		TRY("cudaMalloc(out)", grow_dev_retry(&b->d_out, (size_t)j->chunk * j->page + 64));
+		TRY("cudaMalloc(res)", grow_dev_retry(&b->d_res, (size_t)j->chunk * 8 + 64));
+		TRY("cudaMallocHost(res)", grow_pin(&b->h_res, (size_t)j->chunk * 8 + 64));
+		TRY("cudaMalloc(ctr)", grow_dev_retry(&b->d_ctr, 64));
+	}
+	while (retired < n_mine) {
+		if (j->err)
+			goto out;
+		if (retired < issued && (issued - retired >= PIPE || issued == n_mine)) {
+			struct slot *b = &c->sl[retired % PIPE];
+			const uint32_t *olen = (const uint32_t *)b->h_res.p;
+			const int32_t *st = (const int32_t *)b->h_res.p + b->n;
+			uint64_t produced = 0, bad_page = 0;
+			int bad = 0;
+			uint32_t i;
+			TRY("sync", cudaStreamSynchronize(b->s));
+			for (i = 0; i < b->n; i++) {
+				if (st[i] != 0 && !bad) {
+					bad = st[i];
+					bad_page = b->first + i;
+				}
+				produced += olen[i];
+			}
+			pthread_mutex_lock(&j->mu);
+			j->produced += produced;
+			if (bad && (!j->first_err || bad_page < j->err_page)) {
+				j->first_err = bad;
+				j->err_page = bad_page;
+			}
+			pthread_mutex_unlock(&j->mu);
+			retired++;
 			continue;
 		}
 		{
-			struct bc_slot *b = &BC[issued % BC_PIPE];
-			uint64_t left_pages = nr - done, in_at = done * page_size;
-			uint32_t nb = left_pages < chunk ? (uint32_t)left_pages : chunk;
-			uint64_t in_bytes = input_length - in_at < (uint64_t)nb * page_size ? input_length - in_at
-											      : (uint64_t)nb * page_size;
-			struct csb_compress_args a;
-			TRY("H2D", cudaMemcpyAsync(b->d_in.p, (const uint8_t *)h_in + in_at, in_bytes, cudaMemcpyHostToDevice, b->s));
-			memset(&a, 0, sizeof(a));
-			a.in = (const uint8_t *)b->d_in.p;
-			a.in_stride = page_size;
-			a.uniform_len = page_size;
-			a.total_len = in_bytes;
+			struct slot *b = &c->sl[issued % PIPE];
+			const uint64_t gc = (uint64_t)w->g + issued * (uint64_t)j->G;
+			const uint64_t first = gc * j->chunk, left_pages = j->nr - first;
+			const uint32_t nb = left_pages < j->chunk ? (uint32_t)left_pages : j->chunk;
+			const uint64_t bytes = j->chunk_at[gc + 1] - j->chunk_at[gc];
+			struct csb_decompress_args a;
+			if (bytes)
+				TRY("H2D payload", cudaMemcpyAsync(b->d_packed.p, j->cont + j->chunk_at[gc], bytes, cudaMemcpyHostToDevice, b->s));
+			TRY("H2D index", cudaMemcpyAsync(b->d_clen.p, j->idx + 4 * first, (size_t)nb * 4, cudaMemcpyHostToDevice, b->s));
+			TRY("scan launch", csb_launch_scan((const uint32_t *)b->d_clen.p, nb, (uint64_t *)b->d_off.p, (csb_stream_t)b->s));
+			fill_decompress_args(&a);
+			a.in = (const uint8_t *)b->d_packed.p;
+			a.in_off = (const uint64_t *)b->d_off.p;
+			a.in_len = (const uint32_t *)b->d_clen.p;
 			a.n_blocks = nb;
-			a.out = (uint8_t *)b->d_slots.p;
-			a.out_stride = out_stride;
-			a.out_len = (uint32_t *)b->d_len.p;
-			a.wm = workmem_bytes_power_of_two;
-			a.lanes = g_compress_lanes;
-			a.ctas_per_sm = g_ctas_per_sm;
+			a.out = (uint8_t *)b->d_out.p;
+			a.out_stride = j->page;
+			a.uniform_cap = j->page;
+			a.out_len = (uint32_t *)b->d_res.p;
+			a.status = (int32_t *)b->d_res.p + nb;
+			a.flags = CSNAPPY_BATCH_RAW_IF_FULL;
+			a.max_in_len = j->chunk_longest[gc];
 			a.counter = (uint32_t *)b->d_ctr.p;
-			TRY("compress launch", csb_launch_compress(&a, (csb_stream_t)b->s));
-			TRY("pack launch", csb_launch_pack_stored((const uint8_t *)b->d_slots.p, out_stride, (const uint32_t *)b->d_len.p, nb,
-								  (const uint8_t *)b->d_in.p, page_size, in_bytes, (uint32_t *)b->d_clen.p,
-								  (uint8_t *)b->d_packed.p, (uint64_t *)b->d_off.p, (csb_stream_t)b->s));
-			TRY("D2H total", cudaMemcpyAsync(b->h_res.p, (uint64_t *)b->d_off.p + nb, 8, cudaMemcpyDeviceToHost, b->s));
-			TRY("D2H index", cudaMemcpyAsync(cont + 4 + 4 * done, b->d_clen.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, b->s));
-			TRY("event record", cudaEventRecord(b->ev, b->s));
-			done += nb;
+			TRY("decompress launch", csb_launch_decompress(&a, (csb_stream_t)b->s));
+			TRY("D2H pages", cudaMemcpyAsync(j->out + first * j->page, b->d_out.p, (size_t)nb * j->page, cudaMemcpyDeviceToHost, b->s));
+			TRY("D2H result", cudaMemcpyAsync(b->h_res.p, b->d_res.p, (size_t)nb * 8, cudaMemcpyDeviceToHost, b->s));
+			b->first = first;
+			b->n = nb;
 			issued++;
 		}
 	}
-	for (k = 0; k < BC_PIPE; k++)
-		TRY("sync", cudaStreamSynchronize(BC[k].s));
-	*container_length = payload_pos;
 out:
-	if (rc && bc_ready)
-		for (k = 0; k < BC_PIPE; k++)
-			cudaStreamSynchronize(BC[k].s);
-	pthread_mutex_unlock(&C.mu);
-	return rc;
+	if (c)
+		for (k = 0; k < PIPE; k++)
+			cudaStreamSynchronize(c->sl[k].s);
+	if (rc)
+		djob_fail(j, rc);
+	ctx_release(c);
+	return NULL;
 }
 
-int csnappy_bc_decompress_host(const void *h_container, uint64_t container_length, uint32_t page_size, void *h_out,
-			       uint64_t out_capacity, uint64_t *out_length, uint32_t *failed_page)
+static int bc_decompress(const void *h_container, uint64_t container_length, uint32_t page_size, void *h_out,
+			 uint64_t out_capacity, uint64_t *out_length, uint32_t *failed_page, const int *devs, int G)
 {
-	int rc = 0, k, first_err = 0;
 	const uint8_t *cont = (const uint8_t *)h_container;
-	uint32_t nr32 = 0, chunk, max_clen;
-	uint64_t nr, done, ipos, issued = 0, retire_next = 0, produced_total = 0, err_page = 0;
-	const uint32_t *idx;
+	uint32_t nr32 = 0, max_clen;
+	uint64_t nr, i, ipos, n_chunks;
+	uint64_t *chunk_at = NULL;
+	uint32_t *chunk_longest = NULL;
+	struct djob j;
+	struct dworker w[MAX_DEV];
+	struct hostreg r1, r2;
+	int rc = 0, g, index_err = 0;
+	uint64_t index_err_page = 0;
 	if (page_size == 0 || page_size > CSB_FRAGMENT_MAX)
 		return set_err("page_size outside 1..32768", 0);
 	if (!h_container || !out_length || container_length < 4)
@@ -816,108 +1378,104 @@ int csnappy_bc_decompress_host(const void *h_container, uint64_t container_lengt
 	*out_length = 0;
 	if (nr == 0)
 		return 0;
-	idx = (const uint32_t *)(cont + 4); /* (4-byte aligned if the container is) */
-	ipos = 4 + 4 * nr;
-	chunk = bc_chunk_pages(page_size, nr);
 	max_clen = csnappy_max_compressed_length(page_size);
-
-	pthread_mutex_lock(&C.mu);
-	TRY("stream create", bc_init());
-	for (k = 0; k < BC_PIPE; k++) {
-		struct bc_slot *b = &BC[k];
-		TRY("cudaMalloc(packed)", grow_dev(&b->d_packed, (size_t)chunk * max_clen + 64));
-		TRY("cudaMalloc(clen)", grow_dev(&b->d_clen, (size_t)chunk * 4 + 64));
-		TRY("cudaMalloc(off)", grow_dev(&b->d_off, ((size_t)chunk + 1) * 8 + 64));
-		TRY("cudaMalloc(out)", grow_dev(&b->d_out, (size_t)chunk * page_size + 64));
-		TRY("cudaMalloc(res)", grow_dev(&b->d_res, (size_t)chunk * 8 + 64));
-		TRY("cudaMallocHost(res)", grow_pin(&b->h_res, (size_t)chunk * 8 + 64));
-		TRY("cudaMalloc(ctr)", grow_dev(&b->d_ctr, 64));
-		b->busy = 0;
+	memset(&j, 0, sizeof(j));
+	j.cont = cont;
+	j.idx = cont + 4;
+	j.page = page_size;
+	j.out = (uint8_t *)h_out;
+	j.G = G;
+	j.devs = devs;
+	j.chunk = chunk_units(page_size, nr, G);
+	n_chunks = (nr + j.chunk - 1) / j.chunk;
+	chunk_at = (uint64_t *)malloc((size_t)(n_chunks + 1) * 8);
+	chunk_longest = (uint32_t *)calloc((size_t)n_chunks, 4);
+	if (!chunk_at || !chunk_longest) {
+		free(chunk_at);
+		free(chunk_longest);
+		return set_err("host index", (int)cudaErrorMemoryAllocation);
 	}
-	for (done = 0; done < nr || retire_next < issued;) {
-		if (retire_next < issued && (issued - retire_next >= BC_PIPE || done >= nr)) {
-			struct bc_slot *b = &BC[retire_next % BC_PIPE];
-			const uint32_t *olen = (const uint32_t *)b->h_res.p;
-			const int32_t *st = (const int32_t *)b->h_res.p + b->n;
-			uint32_t i;
-			TRY("sync", cudaStreamSynchronize(b->s));
-			for (i = 0; i < b->n; i++) {
-				if (st[i] != 0 && (!first_err || b->first + i < err_page)) {
-					first_err = st[i];
-					err_page = b->first + i;
-				}
-				produced_total += olen[i];
-			}
-			retire_next++;
-			continue;
+	/* payload positions from the index; a size no writer produces, or a payload past the end of the container,
+	 * ends the decodable prefix (pages before it are still decoded: an earlier failing page wins) */
+	ipos = 4 + 4 * nr;
+	j.nr = nr;
+	for (i = 0; i < nr; i++) {
+		uint32_t cl;
+		if (i % j.chunk == 0)
+			chunk_at[i / j.chunk] = ipos;
+		memcpy(&cl, j.idx + 4 * i, 4);
+		if (cl > max_clen || ipos + cl > container_length) {
+			index_err = CSNAPPY_E_DATA_MALFORMED;
+			index_err_page = i;
+			j.nr = i;
+			break;
 		}
-		{
-			struct bc_slot *b = &BC[issued % BC_PIPE];
-			uint64_t left_pages = nr - done, bytes = 0;
-			uint32_t nb = left_pages < chunk ? (uint32_t)left_pages : chunk, i, longest = 0;
-			struct csb_decompress_args a;
-			for (i = 0; i < nb; i++) {
-				uint32_t cl;
-				memcpy(&cl, (const uint8_t *)idx + 4 * (done + i), 4);
-				if (cl > max_clen || ipos + bytes + cl > container_length) {
-					/* a size no writer produces, or a payload past the end of the container */
-					if (!first_err) {
-						first_err = CSNAPPY_E_DATA_MALFORMED;
-						err_page = done + i;
-					}
-					nb = i;
-					left_pages = 0;
+		if (cl > chunk_longest[i / j.chunk])
+			chunk_longest[i / j.chunk] = cl;
+		ipos += cl;
+	}
+	j.n_chunks = (j.nr + j.chunk - 1) / j.chunk;
+	chunk_at[j.n_chunks] = ipos;
+	j.chunk_at = chunk_at;
+	j.chunk_longest = chunk_longest;
+	pthread_mutex_init(&j.mu, NULL);
+	hostreg_begin(&r1, h_container, container_length);
+	hostreg_begin(&r2, h_out, j.nr * page_size);
+	if (j.n_chunks) {
+		if (!devs) {
+			w[0].j = &j;
+			w[0].g = 0;
+			decompress_worker(&w[0]);
+		} else {
+			int started = 0;
+			for (g = 0; g < G; g++) {
+				w[g].j = &j;
+				w[g].g = g;
+				if (pthread_create(&w[g].th, NULL, decompress_worker, &w[g])) {
+					set_err("pthread_create", (int)cudaErrorUnknown);
+					djob_fail(&j, CSNAPPY_E_DEVICE);
 					break;
 				}
-				bytes += cl;
-				if (cl > longest)
-					longest = cl;
+				started++;
 			}
-			if (nb) {
-				TRY("H2D payload", cudaMemcpyAsync(b->d_packed.p, cont + ipos, bytes, cudaMemcpyHostToDevice, b->s));
-				TRY("H2D index", cudaMemcpyAsync(b->d_clen.p, (const uint8_t *)idx + 4 * done, (size_t)nb * 4, cudaMemcpyHostToDevice, b->s));
-				TRY("scan launch", csb_launch_scan((const uint32_t *)b->d_clen.p, nb, (uint64_t *)b->d_off.p, (csb_stream_t)b->s));
-				memset(&a, 0, sizeof(a));
-				a.in = (const uint8_t *)b->d_packed.p;
-				a.in_off = (const uint64_t *)b->d_off.p;
-				a.in_len = (const uint32_t *)b->d_clen.p;
-				a.n_blocks = nb;
-				a.out = (uint8_t *)b->d_out.p;
-				a.out_stride = page_size;
-				a.uniform_cap = page_size;
-				a.out_len = (uint32_t *)b->d_res.p;
-				a.status = (int32_t *)b->d_res.p + nb;
-				a.flags = CSNAPPY_BATCH_RAW_IF_FULL;
-				a.max_in_len = longest;
-				a.counter = (uint32_t *)b->d_ctr.p;
-				a.lanes = g_decompress_lanes;
-				a.stage_input = g_stage_input;
-				a.smem_kb = g_smem_kb;
-				a.ctas_per_sm = g_ctas_per_sm;
-				TRY("decompress launch", csb_launch_decompress(&a, (csb_stream_t)b->s));
-				TRY("D2H pages", cudaMemcpyAsync((uint8_t *)h_out + done * page_size, b->d_out.p, (size_t)nb * page_size,
-								 cudaMemcpyDeviceToHost, b->s));
-				TRY("D2H result", cudaMemcpyAsync(b->h_res.p, b->d_res.p, (size_t)nb * 8, cudaMemcpyDeviceToHost, b->s));
-				b->first = done;
-				b->n = nb;
-				ipos += bytes;
-				done += nb;
-				issued++;
-			}
-			if (left_pages == 0)
-				done = nr; /* stop queueing after a malformed index entry */
+			for (g = 0; g < started; g++)
+				pthread_join(w[g].th, NULL);
 		}
 	}
-	*out_length = produced_total;
-	if (first_err) {
-		if (failed_page)
-			*failed_page = (uint32_t)err_page;
-		rc = first_err;
+	hostreg_end(&r1);
+	hostreg_end(&r2);
+	pthread_mutex_destroy(&j.mu);
+	free(chunk_at);
+	free(chunk_longest);
+	if (j.err) {
+		memcpy(tls_err, j.errtext, sizeof(tls_err));
+		return j.err;
 	}
-out:
-	if (bc_ready)
-		for (k = 0; k < BC_PIPE; k++)
-			cudaStreamSynchronize(BC[k].s);
-	pthread_mutex_unlock(&C.mu);
+	*out_length = j.produced;
+	if (index_err && (!j.first_err || index_err_page < j.err_page)) {
+		j.first_err = index_err;
+		j.err_page = index_err_page;
+	}
+	if (j.first_err) {
+		if (failed_page)
+			*failed_page = (uint32_t)j.err_page;
+		rc = j.first_err;
+	}
 	return rc;
+}
+
+int csnappy_bc_decompress_host(const void *h_container, uint64_t container_length, uint32_t page_size, void *h_out,
+			       uint64_t out_capacity, uint64_t *out_length, uint32_t *failed_page)
+{
+	return bc_decompress(h_container, container_length, page_size, h_out, out_capacity, out_length, failed_page, NULL, 1);
+}
+
+int csnappy_bc_decompress_host_multi(const void *h_container, uint64_t container_length, uint32_t page_size, void *h_out,
+				     uint64_t out_capacity, uint64_t *out_length, uint32_t *failed_page,
+				     const int *devices, int n_devices)
+{
+	int list[MAX_DEV], G = resolve_devices(devices, n_devices, list);
+	if (G < 0)
+		return G;
+	return bc_decompress(h_container, container_length, page_size, h_out, out_capacity, out_length, failed_page, list, G);
 }

@@ -5,6 +5,7 @@
 #ifndef CSNAPPY_B200_KERNELS_H_
 #define CSNAPPY_B200_KERNELS_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -67,6 +68,15 @@ int csb_launch_pack_stored(const uint8_t *slots, uint64_t slot_stride, const uin
 			   const uint8_t *in, uint32_t page_len, uint64_t total_in, uint32_t *clen,
 			   uint8_t *packed, uint64_t *off, csb_stream_t s);
 int csb_launch_scan(const uint32_t *len, uint32_t n_blocks, uint64_t *off, csb_stream_t s);
+/* batched csnappy_compress framing: header + fragments of every buffer into its output slot (pack_kernel.cu) */
+int csb_launch_frame(const uint8_t *slots, uint64_t slot_stride, const uint32_t *len, const uint64_t *off,
+		     const uint32_t *fbuf, const uint32_t *bfirst, const uint32_t *blen, uint32_t n_frag,
+		     uint32_t n_buffers, uint8_t *out, uint64_t out_stride, uint32_t *out_len, csb_stream_t s);
+/* Parallel decoder of ONE long raw stream (stream_kernel.cu).  aux tables: which = 0 -> per input byte, 1 -> per output
+ * byte.  Returns 0, 1 ("not for this stream": caller falls back to the warp-per-stream path), or a cudaError_t (> 1). */
+size_t csb_stream_aux_bytes(uint32_t src_len, uint32_t cap, int which);
+int csb_launch_decompress_stream(const uint8_t *d_in, uint32_t src_len, uint8_t *d_out, uint32_t cap, uint32_t *d_out_len,
+				 int32_t *d_status, void *d_aux_in, void *d_aux_out, csb_stream_t s);
 uint64_t csb_launch_count(void);
 
 #ifdef __cplusplus

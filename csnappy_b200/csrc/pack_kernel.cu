@@ -159,9 +159,84 @@ __global__ void __launch_bounds__(256) gather_kernel(const uint8_t *__restrict__
 	}
 }
 
+// Framing of csnappy_compress (/root/reference/csnappy_compress.c:621-656) for a BATCH of buffers: fragment f of
+// buffer b = fbuf[f] lands behind that buffer's varint32 header and its earlier fragments.  One warp per fragment
+// moves the bytes; the first fragment's warp (or, for an empty buffer, the buffer's own pseudo-fragment) also
+// writes the header and the buffer's total length.
+//   off[f]      exclusive scan of the fragment sizes over the whole batch
+//   bfirst[b]   index of buffer b's first fragment (bfirst[n_buffers] = n_frag); an empty buffer owns none
+__global__ void __launch_bounds__(256) frame_kernel(const uint8_t *__restrict__ slots, uint64_t stride,
+						    const uint32_t *__restrict__ len, const uint64_t *__restrict__ off,
+						    const uint32_t *__restrict__ fbuf, const uint32_t *__restrict__ bfirst,
+						    const uint32_t *__restrict__ blen, uint32_t n_frag, uint32_t n_buffers,
+						    uint8_t *__restrict__ out, uint64_t out_stride, uint32_t *__restrict__ out_len)
+{
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+	const uint32_t w0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	// headers and totals: one lane per buffer
+	for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < n_buffers; b += gridDim.x * blockDim.x) {
+		uint8_t *o = out + (uint64_t)b * out_stride;
+		uint32_t v = blen[b], k = 0;
+		while (v >= 128) {  // encode_varint32, csnappy_compress.c:46-73
+			o[k++] = (uint8_t)(v | 0x80u);
+			v >>= 7;
+		}
+		o[k++] = (uint8_t)v;
+		out_len[b] = k + (uint32_t)(off[bfirst[b + 1]] - off[bfirst[b]]);
+	}
+	for (uint32_t f = w0; f < n_frag; f += warps) {
+		const uint32_t b = fbuf[f], m = len[f];
+		const uint32_t n = blen[b];
+		const uint32_t hdr = n < (1u << 7) ? 1u : (n < (1u << 14) ? 2u : (n < (1u << 21) ? 3u : (n < (1u << 28) ? 4u : 5u)));
+		const uint8_t *src = slots + (uint64_t)f * stride;
+		uint8_t *dst = out + (uint64_t)b * out_stride + hdr + (off[f] - off[bfirst[b]]);
+		uint32_t head = (uint32_t)((4u - (reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u);
+		if (head > m)
+			head = m;
+		if (lane < head)
+			dst[lane] = src[lane];
+		const uint32_t words = (m - head) >> 2;
+		const uint8_t *s = src + head;
+		const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(s) & 3u);
+		const uint32_t *sw = reinterpret_cast<const uint32_t *>(s - sh);
+		uint32_t *dw = reinterpret_cast<uint32_t *>(dst + head);
+		if (sh == 0) {
+			for (uint32_t w = lane; w < words; w += 32)
+				dw[w] = sw[w];
+		} else {
+			for (uint32_t w = lane; w < words; w += 32)
+				dw[w] = __funnelshift_r(sw[w], sw[w + 1], sh * 8);
+		}
+		const uint32_t tail = head + (words << 2);
+		if (tail + lane < m)
+			dst[tail + lane] = src[tail + lane];
+	}
+}
+
 }  // namespace csb
 
 using namespace csb;
+
+extern "C" int csb_launch_frame(const uint8_t *slots, uint64_t slot_stride, const uint32_t *len, const uint64_t *off,
+				const uint32_t *fbuf, const uint32_t *bfirst, const uint32_t *blen, uint32_t n_frag,
+				uint32_t n_buffers, uint8_t *out, uint64_t out_stride, uint32_t *out_len, csb_stream_t s)
+{
+	DeviceInfo di;
+	int e = device_info(&di);
+	if (e)
+		return e;
+	if (n_buffers == 0)
+		return 0;
+	long units = n_frag > n_buffers / 32 ? (long)n_frag : (long)n_buffers / 32 + 1;
+	long ctas = (units + 7) / 8;
+	if (ctas > (long)di.sm_count * 8)
+		ctas = (long)di.sm_count * 8;
+	frame_kernel<<<(int)ctas, 256, 0, s>>>(slots, slot_stride, len, off, fbuf, bfirst, blen, n_frag, n_buffers, out, out_stride,
+					       out_len);
+	count_launch();
+	return (int)cudaGetLastError();
+}
 
 extern "C" uint64_t csb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 

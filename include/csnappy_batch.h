@@ -79,6 +79,25 @@ int csnappy_batch_decompress(const void *d_in, const uint64_t *d_in_off,
 			     void *stream);
 
 /*
+ * Batched csnappy_compress (csnappy_compress.c:621-656): n_buffers WHOLE buffers, each framed exactly like one
+ * csnappy_compress() call -- varint32 length, one fragment per 32 KiB chunk, the short last chunk with the
+ * reference's smaller-table rule (:638-646) -- in one call: all fragments of all buffers are compressed by one
+ * launch, then headers and fragments are packed into each buffer's output slot.
+ *   buffer i        d_in + (h_in_off ? h_in_off[i] : i * in_stride), h_in_len[i] bytes (NULL: uniform_in_len)
+ *   output i        d_out + i * out_stride, d_out_len[i] <- its length;
+ *                   out_stride >= 5 + n + n/6 + 32 * ceil(n / 32768) for the longest buffer
+ * The lengths (and offsets) are HOST arrays: the fragment table is laid out on the host.  d_workspace must hold
+ * csnappy_batch_compress_workspace(...) bytes (fragment slots, sizes, tables) and stay untouched until the
+ * work on `stream` has finished.
+ */
+uint64_t csnappy_batch_compress_workspace(const uint32_t *h_in_len, uint32_t uniform_in_len, uint32_t n_buffers);
+int csnappy_batch_compress(const void *d_in, const uint64_t *h_in_off, uint64_t in_stride,
+			   const uint32_t *h_in_len, uint32_t uniform_in_len, uint32_t n_buffers,
+			   void *d_out, uint64_t out_stride, uint32_t *d_out_len,
+			   int workmem_bytes_power_of_two, void *d_workspace,
+			   uint64_t workspace_bytes, void *stream);
+
+/*
  * Exclusive scan of d_len[0..n) into d_off[0..n] (d_off[n] = total) and
  * gather of the strided slots into one contiguous payload:
  *     d_packed[d_off[i] .. d_off[i]+d_len[i]) = d_slots[i*slot_stride ..)
@@ -133,15 +152,37 @@ int csnappy_bc_decompress_host(const void *h_container, uint64_t container_lengt
 			       uint64_t *out_length, uint32_t *failed_page);
 
 /*
+ * The same container over SEVERAL devices from one process (static sharding, per-device streams,
+ * the host gathers the u32 size arrays and prefix-sums them into one container): the page range is cut into chunks,
+ * chunk c is handled by devices[c mod n_devices] on that device's own worker thread and streams; there is no
+ * data-path collective -- the only thing that crosses devices is the running payload position (8 bytes per chunk).
+ * devices == NULL: devices 0 .. n_devices-1; n_devices == 0: every visible device.  The bytes produced are
+ * identical to the single-device call.  The caller's current device is not changed.
+ */
+int csnappy_bc_compress_host_multi(const void *h_in, uint64_t input_length, uint32_t page_size,
+				   void *h_container, uint64_t container_capacity,
+				   uint64_t *container_length, int workmem_bytes_power_of_two,
+				   const int *devices, int n_devices);
+int csnappy_bc_decompress_host_multi(const void *h_container, uint64_t container_length,
+				     uint32_t page_size, void *h_out, uint64_t out_capacity,
+				     uint64_t *out_length, uint32_t *failed_page,
+				     const int *devices, int n_devices);
+
+/*
  * Library / device introspection and kernel tuning knobs (used by bench.py and
  * the tests; not needed by drop-in callers).
  */
 int csnappy_b200_device_ok(void);	   /* 1 if a CUDA device is usable */
+int csnappy_b200_device_count(void);	   /* visible CUDA devices (0 on error) */
 const char *csnappy_b200_last_error(void); /* text of the last device error (thread local) */
 uint64_t csnappy_b200_kernel_launches(void); /* kernels launched by this library so far */
 /* key: "compress_lanes" | "decompress_lanes" (lanes cooperating on one block: 8/16/32),
  *      "ctas_per_sm", "decompress_stage_input" (1: always stage blocks in shared memory, 2: stage only
  *      the output and read compressed blocks through L1, 3: never stage -- decode against global memory), "decompress_smem_kb" (shared memory per SM in unstaged mode);
+ *      4: one lane per block (the default for very large batches);
+ *      "host_register" (1: page-lock the caller's buffers for the duration of a host-buffer call: worth it for big
+ *      pageable buffers that are reused), "stream_decode_min" (bytes from which one single stream takes the parallel
+ *      stream decoder; -1: never);
  *      value 0 restores the default.  Returns 0 or CSNAPPY_E_BAD_ARG. */
 int csnappy_b200_set_tuning(const char *key, int value);
 

@@ -102,6 +102,26 @@ int main(int argc, char **argv)
 		CHECK(csnappy_bc_decompress_host(cont, cl, 4096, back, (uint64_t)nr_pages * 4096, &ol, NULL) == 0);
 		CHECK(ol == n && memcmp(back, in, n) == 0);
 	}
+	/* the same container over every visible device from this one process, and over device 0 listed
+	 * twice (two workers, two contexts: the chunk-position hand-over without needing two GPUs) */
+	{
+		uint64_t cap = csnappy_bc_max_container_length(n, 4096), cl = 0, cl2 = 0, cl3 = 0, ol = 0;
+		char *c1 = malloc(cap), *c2 = malloc(cap), *c3 = malloc(cap);
+		const int twice[2] = {0, 0};
+		uint32_t nr_pages = (n + 4095) / 4096;
+		CHECK(csnappy_b200_device_count() >= 1);
+		CHECK(csnappy_bc_compress_host(in, n, 4096, c1, cap, &cl, 13) == 0);
+		CHECK(csnappy_bc_compress_host_multi(in, n, 4096, c2, cap, &cl2, 13, NULL, 0) == 0);
+		CHECK(csnappy_bc_compress_host_multi(in, n, 4096, c3, cap, &cl3, 13, twice, 2) == 0);
+		CHECK(cl2 == cl && memcmp(c1, c2, cl) == 0);
+		CHECK(cl3 == cl && memcmp(c1, c3, cl) == 0);
+		memset(back, 0, (size_t)nr_pages * 4096);
+		CHECK(csnappy_bc_decompress_host_multi(c2, cl2, 4096, back, (uint64_t)nr_pages * 4096, &ol, NULL, NULL, 0) == 0);
+		CHECK(ol == n && memcmp(back, in, n) == 0);
+		memset(back, 0, (size_t)nr_pages * 4096);
+		CHECK(csnappy_bc_decompress_host_multi(c3, cl3, 4096, back, (uint64_t)nr_pages * 4096, &ol, NULL, twice, 2) == 0);
+		CHECK(ol == n && memcmp(back, in, n) == 0);
+	}
 	printf("dropin ok: %u -> %u bytes, %llu kernels launched\n", n, clen, (unsigned long long)csnappy_b200_kernel_launches());
 	return 0;
 }

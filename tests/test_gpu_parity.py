@@ -472,3 +472,84 @@ def test_config4_decode_only_of_a_packed_corpus(cs, chk):
     torch.cuda.synchronize()
     assert int((status != 0).sum()) == 0 and int((out_len != L).sum()) == 0
     assert (out.cpu().numpy().reshape(n, L) == corpus).all()
+
+
+# --------------------------------------------------------------------------- round 2 additions to the boundary
+def test_batch_compress_whole_buffers_with_header(cs, chk, urls):
+    """csnappy_batch_compress: many WHOLE buffers per call, each framed like csnappy_compress
+    (csnappy_compress.c:621-656) -- byte-identical to the reference per buffer, at several table sizes."""
+    rng = np.random.default_rng(41)
+    text = bytes(rng.integers(97, 102, 120000, dtype=np.uint8))
+    bufs = [b"", b"a", text[:14], text[:15], text[:100], text[:32767], text[:32768], text[:32769], text[:70001],
+            urls[:100000], bytes(50000), rng.integers(0, 256, 40000, dtype=np.uint8).tobytes(), urls]
+    offs, pos = [], 0
+    for b in bufs:
+        offs.append(pos)
+        pos += len(b) + 3  # arbitrary alignment of every buffer
+    host = np.zeros(pos + 16, dtype=np.uint8)
+    for o, b in zip(offs, bufs):
+        host[o:o + len(b)] = np.frombuffer(b, dtype=np.uint8)
+    d_in = torch.from_numpy(host).cuda()
+    for wm in (9, 13, 15, 16):
+        out, out_len, stride = cs.api.batch_compress(d_in, offs, [len(b) for b in bufs], wm)
+        o, ol = out.cpu().numpy(), out_len.cpu().numpy()
+        for i, b in enumerate(bufs):
+            assert o[i * stride: i * stride + ol[i]].tobytes() == chk.compress(b, wm), (i, len(b), wm)
+
+
+def test_bc_container_multi_device_entry_points(cs, chk, urls):
+    """csnappy_bc_*_host_multi from ONE process: all visible devices, and device 0 listed three times (three workers and
+    contexts exercise the chunk-position hand-over on a single GPU).  Bytes identical to the single-device writer."""
+    from csnappy_b200 import synth
+
+    B, page = 30000, 4096
+    h_in = synth.mixed_pages(B, page, seed=78, device="cuda", pool_bytes=1 << 20).cpu().numpy()
+    cap = cs.api.bc_max_container_length(B * page, page)
+    ref = np.zeros(cap, dtype=np.uint8)
+    clen = cs.api.bc_compress_host(h_in, B * page, ref, 13, page)
+    for devices in (None, [0, 0, 0]):
+        cont = np.zeros(cap, dtype=np.uint8)
+        assert cs.api.bc_compress_host_multi(h_in, B * page, cont, 13, page, devices=devices) == clen
+        assert (cont[:clen] == ref[:clen]).all()
+        out = np.zeros(B * page, dtype=np.uint8)
+        assert cs.api.bc_decompress_host_multi(cont, clen, out, page, devices=devices) == (0, B * page, None)
+        assert (out == h_in).all()
+    # a corrupted page is reported by index through the multi-device reader too
+    idx = ref[4:4 + 4 * B].view(np.uint32)
+    off = 4 + 4 * B + np.concatenate([[0], np.cumsum(idx.astype(np.int64))])
+    victim = next(i for i in range(17000, B) if 100 < idx[i] < page)
+    broken = ref[:clen].copy()
+    broken[off[victim] + 1: off[victim] + 40] = 0xFF
+    out = np.zeros(B * page, dtype=np.uint8)
+    rc, _, bad = cs.api.bc_decompress_host_multi(broken, clen, out, page, devices=[0, 0])
+    assert rc == chk.decompress_noheader(broken[off[victim]: off[victim + 1]].tobytes(), page)[0] != 0 and bad == victim
+
+
+def test_dropin_large_buffer_pipeline_and_concurrent_callers(cs, chk, urls):
+    """csnappy_compress of a multi-chunk buffer goes through the chunk pipeline; concurrent callers on disjoint buffers
+    (the reference is re-entrant, csnappy.h:46-72) each get their own staging context and the same bytes."""
+    import threading
+
+    big = (urls * 14)[: 9 * 1024 * 1024 + 12345]  # > 8 MiB: several pipeline chunks
+    c = cs.csnappy_compress(big, 15)
+    assert c == chk.compress(big, 15)
+    assert cs.csnappy_decompress(c, len(big)) == (0, big)
+    inputs = [urls[i * 1000: i * 1000 + 150000 + 777 * i] for i in range(8)]
+    want = [chk.compress(x, 16) for x in inputs]
+    got = [None] * len(inputs)
+    back = [None] * len(inputs)
+
+    def work(i):
+        for _ in range(3):
+            got[i] = cs.csnappy_compress(inputs[i], 16)
+            back[i] = cs.csnappy_decompress(got[i], len(inputs[i]))
+            page = cs.csnappy_compress_fragment(inputs[i][:4096], 13)
+            assert page == chk.compress_fragment(inputs[i][:4096], 13)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(inputs))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert got == want
+    assert back == [(0, x) for x in inputs]
