@@ -39,6 +39,8 @@ def _declare(L):
         "csnappy_batch_compress": (i, [vp, vp, u64, vp, u32, u32, vp, u64, vp, i, vp, u64, vp]),
         "csnappy_bc_compress_host_multi": (i, [vp, u64, u32, vp, u64, C.POINTER(C.c_uint64), i, vp, i]),
         "csnappy_bc_decompress_host_multi": (i, [vp, u64, u32, vp, u64, C.POINTER(C.c_uint64), _u32p, vp, i]),
+        "csnappy_stream_decompress_workspace": (u64, [u32, u32]),
+        "csnappy_stream_decompress": (i, [vp, u32, vp, u32, vp, vp, vp, u64, vp]),
         "csnappy_b200_device_count": (i, []),
         "csnappy_b200_device_ok": (i, []),
         "csnappy_b200_last_error": (C.c_char_p, []),

@@ -274,6 +274,24 @@ def batch_compress(d_in, in_off, in_len, wm: int, *, out_stride: int | None = No
     return out, out_len, out_stride
 
 
+def stream_decompress(d_src, src_len: int, out_cap: int, *, out=None, workspace=None, result=None):
+    """ONE long raw stream, device resident, through the parallel stream decoder.
+    Returns (out uint8 [out_cap], result int32 [2] = [out_len, status]) CUDA tensors (asynchronous)."""
+    import torch
+
+    ws_bytes = lib().csnappy_stream_decompress_workspace(src_len, out_cap)
+    if workspace is None:
+        workspace = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=d_src.device)
+    if out is None:
+        out = torch.empty(max(out_cap, 16), dtype=torch.uint8, device=d_src.device)
+    if result is None:
+        result = torch.empty(2, dtype=torch.int32, device=d_src.device)
+    rc = lib().csnappy_stream_decompress(_ptr(d_src), src_len, _ptr(out), out_cap, result.data_ptr(),
+                                         result.data_ptr() + 4, _ptr(workspace), workspace.numel(), _stream_ptr())
+    _check(rc, "csnappy_stream_decompress")
+    return out, result
+
+
 def device_count() -> int:
     return lib().csnappy_b200_device_count()
 

@@ -344,6 +344,44 @@ int csnappy_batch_compress(const void *d_in, const uint64_t *h_in_off, uint64_t 
 	return e ? set_err("frame launch", e) : 0;
 }
 
+/* ---- one long raw stream, device resident: the parallel stream decoder (stream_kernel.cu) ---------------- */
+uint64_t csnappy_stream_decompress_workspace(uint32_t src_len, uint32_t out_cap)
+{
+	return (uint64_t)csb_stream_aux_bytes(src_len, out_cap, 0) + (uint64_t)csb_stream_aux_bytes(src_len, out_cap, 1);
+}
+
+int csnappy_stream_decompress(const void *d_src, uint32_t src_len, void *d_dst, uint32_t out_cap, uint32_t *d_out_len,
+			      int32_t *d_status, void *d_workspace, uint64_t workspace_bytes, void *stream)
+{
+	const size_t t1 = csb_stream_aux_bytes(src_len, out_cap, 0);
+	int e;
+	if (!d_out_len || !d_status || !d_workspace || (src_len && !d_src) || (out_cap && !d_dst))
+		return set_err("null buffer", 0);
+	if (workspace_bytes < csnappy_stream_decompress_workspace(src_len, out_cap))
+		return set_err("workspace smaller than csnappy_stream_decompress_workspace()", 0);
+	e = csb_launch_decompress_stream((const uint8_t *)d_src, src_len, (uint8_t *)d_dst, out_cap, d_out_len, d_status, d_workspace,
+					 (uint8_t *)d_workspace + t1, (csb_stream_t)stream);
+	if (e == 1) {
+		/* empty stream, or no cooperative launch on this device: the serial path of the batched decoder */
+		struct csb_decompress_args a;
+		uint32_t *d_len = (uint32_t *)d_workspace;
+		if ((e = (int)cudaMemcpyAsync(d_len, &src_len, 4, cudaMemcpyHostToDevice, (cudaStream_t)stream)))
+			return set_err("H2D len", e);
+		fill_decompress_args(&a);
+		a.stage_input = 3;
+		a.in = (const uint8_t *)d_src;
+		a.in_len = d_len;
+		a.n_blocks = 1;
+		a.out = (uint8_t *)d_dst;
+		a.uniform_cap = out_cap;
+		a.out_len = d_out_len;
+		a.status = d_status;
+		a.max_in_len = src_len;
+		e = csb_launch_decompress(&a, (csb_stream_t)stream);
+	}
+	return e ? set_err("stream decoder launch", e) : 0;
+}
+
 /* ---- staging contexts for the host-pointer calls ------------------------ */
 struct buf {
 	void *p;
@@ -910,7 +948,7 @@ static int decompress_host(const uint8_t *src, uint32_t src_len, uint8_t *dst, u
 	/* one long stream */
 	{
 		struct hostreg r1, r2;
-		const int use_stream = g_stream_min >= 0 && src_len >= (uint32_t)(g_stream_min ? g_stream_min : 16384);
+		const int use_stream = g_stream_min >= 0 && src_len >= (uint32_t)g_stream_min;
 		TRY("cudaMalloc(in)", grow_dev_retry(&sl->d_in, (size_t)src_len + 64));
 		TRY("cudaMalloc(out)", grow_dev_retry(&sl->d_out, (size_t)cap + 64));
 		TRY("cudaMalloc(res)", grow_dev_retry(&sl->d_res, 64));

@@ -98,6 +98,18 @@ int csnappy_batch_compress(const void *d_in, const uint64_t *h_in_off, uint64_t 
 			   uint64_t workspace_bytes, void *stream);
 
 /*
+ * ONE long raw stream, device resident (csnappy_decompress_noheader semantics, csnappy_decompress.c:319-387):
+ * tag starts by speculative parsing + pointer jumping, back-references by pointer jumping over the output
+ * (stream_kernel.cu) instead of a serial tag walk.  This is what the host-pointer csnappy_decompress /
+ * csnappy_decompress_noheader use for streams above 64 KiB.  d_workspace: csnappy_stream_decompress_workspace()
+ * bytes (8 per input byte + 4 per output byte).  *d_status <- 0 / -3 / -5, *d_out_len <- bytes produced (0 on error).
+ */
+uint64_t csnappy_stream_decompress_workspace(uint32_t src_len, uint32_t out_cap);
+int csnappy_stream_decompress(const void *d_src, uint32_t src_len, void *d_dst, uint32_t out_cap,
+			      uint32_t *d_out_len, int32_t *d_status, void *d_workspace,
+			      uint64_t workspace_bytes, void *stream);
+
+/*
  * Exclusive scan of d_len[0..n) into d_off[0..n] (d_off[n] = total) and
  * gather of the strided slots into one contiguous payload:
  *     d_packed[d_off[i] .. d_off[i]+d_len[i]) = d_slots[i*slot_stride ..)

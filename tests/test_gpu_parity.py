@@ -553,3 +553,48 @@ def test_dropin_large_buffer_pipeline_and_concurrent_callers(cs, chk, urls):
         t.join()
     assert got == want
     assert back == [(0, x) for x in inputs]
+
+
+@pytest.mark.parametrize("stream_min", [0, -1])
+def test_single_long_streams_parallel_decoder_vs_oracle(cs, chk, urls, urls_snappy, baddata3, unaligned_pair, stream_min):
+    """f-4: ONE long stream through the drop-in csnappy_decompress_noheader / csnappy_decompress -- the parallel
+    stream decoder (stream_kernel.cu; stream_min 0) and the serial warp-per-stream path (-1) against the oracle:
+    fixtures, multi-fragment streams of every entropy class, corrupted / truncated / extended / under-sized."""
+    uu_s, uu_b = unaligned_pair
+    rng = np.random.default_rng(77)
+    cs.set_tuning("stream_decode_min", stream_min)
+    try:
+        rc, out = cs.csnappy_decompress(urls_snappy, len(urls))
+        assert rc == 0 and out == urls
+        assert cs.csnappy_decompress(baddata3, 130378)[0] == -5
+        rc, out = cs.csnappy_decompress(uu_s, len(uu_b))
+        assert rc == 0 and out == uu_b
+        assert cs.csnappy_decompress(urls_snappy, len(urls) - 1)[0] == cs.CSNAPPY_E_OUTPUT_INSUF
+        bodies = []
+        for k, page in enumerate(fuzz_pages(606, 14, 90000 + 7777)):
+            data = page + urls[k * 5000: k * 5000 + 70000] + bytes(3000 * (k % 3)) + page[:20000]
+            bodies.append((data, chk.compress(data, 15 if k % 2 else 16)))
+        cases = []
+        for k, (data, comp) in enumerate(bodies):
+            hlen, n = chk.get_uncompressed_length(comp)
+            raw = comp[hlen:]
+            cases.append((raw, n))  # valid
+            cases.append((raw, n - 1 - int(rng.integers(0, n // 2))))  # under-sized: -3 somewhere
+            d = bytearray(raw)
+            for _ in range(1 + k % 3):
+                d[int(rng.integers(0, len(d)))] ^= int(rng.integers(1, 256))
+            cases.append((bytes(d), n))  # flipped bytes
+            cases.append((raw[: int(rng.integers(len(raw) // 2, len(raw)))], n))  # truncated
+            cases.append((raw + bytes(rng.integers(0, 256, 5, dtype=np.uint8)), n + 300))  # extended
+        n_err = 0
+        for i, (s, cap) in enumerate(cases):
+            rc, exp = oracle.port().decompress_noheader(s, cap)
+            got_rc, got = cs.csnappy_decompress_noheader(s, cap)
+            assert got_rc == rc, (i, stream_min, len(s), cap)
+            if rc == 0:
+                assert got == exp, (i, stream_min)
+            else:
+                n_err += 1
+        assert n_err >= len(cases) // 3
+    finally:
+        cs.set_tuning("stream_decode_min", 0)
