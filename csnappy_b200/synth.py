@@ -3,7 +3,7 @@
 zram-style batch: pages of `page_len` bytes, class per page from
 splitmix64(seed ^ page_index): 50 % text, 25 % zero, 25 % random.
   text    text="urls": a page_len slice of the reference's urls.10K corpus (committed copy:
-          tests/golden/urls.10K.gz) at offset h mod (702087 - page_len) -- the primary definition
+          csnappy_b200/data/urls.10K.gz) at offset h mod (702087 - page_len) -- the primary definition
           of SURVEY.md 8d config 2;  text="words": the purely synthetic alternative, a page_len
           slice of a Zipf(1.1) word stream over a 4096-word lowercase vocabulary
   zero    all zero bytes
@@ -51,12 +51,12 @@ def text_pool(nbytes: int, seed: int = 0x5EED0002) -> np.ndarray:
 
 
 def urls_pool() -> np.ndarray:
-    """The reference's own text corpus (testdata/urls.10K, committed as tests/golden/urls.10K.gz): the
+    """The reference's own text corpus (testdata/urls.10K, committed as csnappy_b200/data/urls.10K.gz): the
     primary text class of SURVEY.md 8d config 2 is a 4096-byte slice of it at a seeded offset."""
     import gzip
     import os
 
-    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "urls.10K.gz")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "urls.10K.gz")
     with gzip.open(path, "rb") as f:
         return np.frombuffer(f.read(), dtype=np.uint8).copy()
 
