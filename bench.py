@@ -19,10 +19,15 @@ the max-over-ranks only.
 `value`      device-resident: inputs already in HBM, CUDA events around K steps.
 `e2e`        same metric through the host-buffer C-ABI (csnappy_batch_*_host) with pinned
              host buffers: H2D of every page and D2H of every result inside the timed region.
+`e2e_pageable` the same calls on ordinary (pageable) caller memory.
 `roofline`   dominant kernel (compress) against the measured HBM copy peak;
              algorithmic bytes = sum N_in + sum C_out + 4 B.
+`workloads`  BASELINE.json configs[2] and [3], device-resident, every rank, reduced like `value`:
+             fragments_32k (32 KiB text fragments, wm 15 and 16, 4 GiB per GPU, seed 0x5EED0002) and decode_only
+             (a pre-compressed corpus of 64 GiB per GPU in 16 GiB waves, 4 KiB mixed pages and 32 KiB text
+             fragments, seed 0x5EED0003), each with its own roofline fraction and a sample checked against the CPU reference.
 `cpu_baseline` the unmodified reference (oracle/_ref) or the oracle port on this box's cores.
---impl reference times that CPU implementation alone, on a bounded sample per step.
+--impl reference times that CPU implementation alone (same config, same protocol: oracle.BatchRunner.measure).
 """
 from __future__ import annotations
 
@@ -113,60 +118,180 @@ class ClockSampler:
         return out
 
 
-def cpu_codec_pass(host_pages, threads: int, impl: str, repeats: int = 3):
-    """compress + decompress `host_pages` [S, PAGE] on the CPU.  -> (best_comp_s, best_dec_s, out, lens)"""
-    import numpy as np
+def workload_config(text: str, pages: int, world: int, ratio):
+    """`config` of the JSON line -- the SAME dict in both arms (the driver compares them)."""
+    return {"workload": f"zram-style batch: synthetic 4 KiB pages (50% text [{TEXT_DESC[text]}] / 25% zero / "
+                        "25% random), wm 13, compress then decompress", "pages_per_gpu": pages, "page_bytes": PAGE,
+            "wm": WM, "ratio": ratio, "parallelism": f"shard{world} (no collective)",
+            "l2": "inputs (4 GiB per GPU) exceed the 126 MB L2; no explicit flush",
+            "value_definition": "(bytes compressed + bytes decompressed) / step time"}
 
+
+def cpu_measure(host_units, wm: int, warmup: int, steps: int):
+    """The one CPU-baseline protocol (both arms): the reference's codec on all host cores over `host_units`
+    [S, unit], buffers allocated and touched once, mean of `steps` passes after `warmup` passes.
+    -> (runner, compress_s, decompress_s, impl, cores)"""
     import oracle
-
-    best_c = best_d = float("inf")
-    out = lens = None
-    for _ in range(repeats):
-        out, lens, sc = oracle.batch_compress(host_pages, WM, impl, threads=threads)
-        best_c = min(best_c, sc)
-    for _ in range(repeats):
-        back, blen, st, sd = oracle.batch_decompress(out, lens, PAGE, impl, threads=threads)
-        best_d = min(best_d, sd)
-    assert (st == 0).all() and (blen == PAGE).all() and (back[:, :PAGE] == host_pages).all()
-    return best_c, best_d, out, lens
-
-
-def run_reference(args, rank: int, world: int):
-    """--impl reference: the reference's own CPU implementation on this box's cores."""
-    if rank != 0:
-        return
-    import numpy as np
-    import torch
-
-    import oracle
-    from csnappy_b200 import synth
 
     impl = "reference" if oracle.have_reference() else "port"
     cores = host_cores()
-    S = min(args.pages, 1 << 16)  # bounded sample per step: 64 Ki pages = 256 MiB
+    r = oracle.BatchRunner(host_units, wm, impl, threads=cores)
+    tc, td = r.measure(warmup, steps)
+    return r, tc, td, impl, cores
+
+
+def run_reference(args, rank: int, world: int):
+    """--impl reference: the reference's own CPU implementation on this box's cores, on rank 0's shard of the
+    same workload (all `--pages` pages per step unless --cpu-pages bounds the sample)."""
+    if rank != 0:
+        return
+    import torch
+
+    from csnappy_b200 import synth
+
+    S = min(args.pages, args.cpu_pages) if args.cpu_pages else args.pages
     dev = "cuda" if torch.cuda.is_available() else "cpu"
     pages = synth.mixed_pages(S, PAGE, seed=SEED, device=dev, text=args.text).view(S, PAGE).cpu().numpy()
-    times = []
-    for it in range(args.warmup + args.steps):
-        tc, td, _, _ = cpu_codec_pass(pages, cores, impl, repeats=1)
-        if it >= args.warmup:
-            times.append(tc + td)
-    total = sum(times)
-    value = 2 * S * PAGE * args.steps / total / 1e9
+    r, tc, td, impl, cores = cpu_measure(pages, WM, args.warmup, args.steps)
+    value = 2 * S * PAGE / (tc + td) / 1e9
+    ratio = round(float(r.comp_len.sum(dtype="uint64")) / (S * PAGE), 4)
     line = {
         "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": "GB/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * total / args.steps, 3),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * (tc + td), 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"zram-style batch: synthetic 4 KiB pages (50% text [{TEXT_DESC[args.text]}] / 25% zero / "
-                               "25% random), wm 13, compress then decompress", "pages_per_gpu": args.pages,
-                   "page_bytes": PAGE, "wm": WM},
+        "config": workload_config(args.text, args.pages, args.gpus, ratio),
+        "compress_gbs": round(S * PAGE / tc / 1e9, 3), "decompress_gbs": round(S * PAGE / td / 1e9, 3),
         "cpu_baseline": {"value": round(value, 3), "unit": "GB/s", "cores": cores, "kind": impl,
-                         "sample": f"{S} pages ({S * PAGE >> 20} MiB) per step, compress + decompress, "
-                                   f"{cores} pthreads, static partition"},
+                         "sample": f"{S} pages ({S * PAGE >> 20} MiB) per step = rank 0's shard, compress + decompress, "
+                                   f"{cores} pthreads, static partition, mean of {args.steps} steps after {args.warmup} warm-ups"},
         "e2e": {"value": round(value, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def run_workloads(args, cs, synth, dev, rank, world, barrier):
+    """BASELINE.json configs[2] "32 KB fragments over a text-like stream" and configs[3] "decompression-only throughput
+    of a pre-compressed corpus" (SURVEY.md 8d configs 3 and 4).  Weak scaling like the main workload: every rank owns
+    its own range of the global fragment / page sequence.  Times are CUDA events on the launching stream, max over
+    ranks; bytes are summed over ranks.  Each shape is checked: exact round trip of everything, and the compressed
+    bytes of a sample against the CPU reference (oracle/, the checker -- never the thing timed)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import oracle
+
+    peak, _ = measured_peak()
+    impl = "reference" if oracle.have_reference() else "port"
+    FRAG = 32768
+
+    def timed(fn, reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    def reduce(ms_list, sums):
+        v = torch.tensor(ms_list, dtype=torch.float64, device=dev)
+        t = torch.tensor(sums, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(v, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return v.tolist(), t.tolist()
+
+    def check_sample(units2d, unit, wm, comp, comp_len, ostride, k=64):
+        """compressed bytes of k units spread over the batch == the CPU reference's"""
+        n = units2d.shape[0]
+        idx = np.unique(np.linspace(0, n - 1, k).astype(np.int64))
+        ti = torch.from_numpy(idx).to(dev)
+        host = units2d.index_select(0, ti).cpu().numpy()
+        r = oracle.BatchRunner(host, wm, impl, threads=min(host_cores(), len(idx)))
+        r.compress()
+        got_len = comp_len.index_select(0, ti).cpu().numpy().astype(np.uint32)
+        got = comp.view(n, ostride).index_select(0, ti).cpu().numpy()
+        assert (got_len == r.comp_len).all(), "compressed sizes differ from the CPU reference"
+        for j in range(len(idx)):
+            assert got[j, : got_len[j]].tobytes() == r.compressed(j), f"compressed bytes of unit {idx[j]} differ"
+        return len(idx)
+
+    def codec_pass(data, unit, n, wm, reps_c, reps_d, bufs):
+        """compress (timed reps_c times) + decompress (timed reps_d times) of n units; -> ms_c, ms_d, csum"""
+        comp, comp_len, back, back_len, status, ostride = bufs
+        cfn = lambda: cs.batch_compress_fragments(data, unit, n, wm, out=comp, out_len=comp_len, out_stride=ostride)
+        dfn = lambda: cs.batch_decompress(comp, comp_len, n, unit, in_stride=ostride, out=back, out_stride=unit,
+                                          out_len=back_len, status=status)
+        cfn()  # warm-up; also what the decoder reads
+        ms_c = timed(cfn, reps_c) if reps_c else None
+        dfn()
+        ms_d = timed(dfn, reps_d)
+        assert int((status[:n] != 0).sum()) == 0 and int((back_len[:n] != unit).sum()) == 0
+        assert torch.equal(back[: n * unit], data), "round trip mismatch"
+        return ms_c, ms_d, float(comp_len[:n].sum(dtype=torch.int64))
+
+    def alloc(unit, n):
+        ostride = cs.api.out_stride_for(unit)
+        return (torch.empty(n * ostride, dtype=torch.uint8, device=dev), torch.empty(n, dtype=torch.int32, device=dev),
+                torch.empty(n * unit, dtype=torch.uint8, device=dev), torch.empty(n, dtype=torch.int32, device=dev),
+                torch.empty(n, dtype=torch.int32, device=dev), ostride)
+
+    out = {}
+    # ---- fragments_32k: block_compressor / csnappy_compress fragments of a text-like stream -------------------------
+    n = max(1, int(args.frag_gib * (1 << 30)) // FRAG)
+    data = synth.text_fragments(n, FRAG, seed=0x5EED0002, device=dev, first=rank * n)
+    bufs = alloc(FRAG, n)
+    frag = {"unit_bytes": FRAG, "units_per_gpu": n, "seed": "0x5EED0002",
+            "data": "32 KiB slices of the Zipf word stream at seeded offsets (synth.text_fragments)"}
+    for wm in (15, 16):
+        ms_c, ms_d, csum = codec_pass(data, FRAG, n, wm, 2, 3, bufs)
+        checked = check_sample(data.view(n, FRAG), FRAG, wm, bufs[0], bufs[1], bufs[5])
+        (ms_c, ms_d), (tot_n, tot_c) = reduce([ms_c, ms_d], [float(n) * FRAG, csum])
+        alg_c, alg_d = n * FRAG + tot_c / world + 4 * n, tot_c / world + n * FRAG + 8 * n
+        frag[f"wm{wm}"] = {"ratio": round(tot_c / tot_n, 4),
+                           "compress_gbs": round(tot_n / ms_c / 1e6, 2), "decompress_gbs": round(tot_n / ms_d / 1e6, 2),
+                           "compress_ms": round(ms_c, 3), "decompress_ms": round(ms_d, 3),
+                           "roofline_frac_compress": round(alg_c / ms_c / 1e6 / peak, 4),
+                           "roofline_frac_decompress": round(alg_d / ms_d / 1e6 / peak, 4),
+                           "units_checked_against_cpu_reference": checked}
+    out["fragments_32k"] = frag
+    del data, bufs
+    torch.cuda.empty_cache()
+
+    # ---- decode_only: a pre-compressed corpus, decoded in waves ---------------------------------------------------
+    # The corpus is compressed on the device by the kernels whose output is byte-identical to the reference's
+    # (tests/, and the per-wave sample check below); only the decode passes are timed.
+    dec = {"seed": "0x5EED0003", "corpus_gib_per_gpu": args.decode_gib, "wave_gib": args.wave_gib}
+    for name, unit, wm in (("pages_4k", PAGE, WM), ("fragments_32k", FRAG, 15)):
+        wave_units = max(1, int(args.wave_gib * (1 << 30)) // unit)
+        waves = max(1, int(round(args.decode_gib / args.wave_gib)))
+        bufs = alloc(unit, wave_units)
+        ms_sum, n_sum, c_sum, checked = 0.0, 0.0, 0.0, 0
+        for w in range(waves):
+            first = (rank * waves + w) * wave_units
+            if unit == PAGE:
+                data = synth.mixed_pages(wave_units, PAGE, seed=0x5EED0003, device=dev, first_page=first, text=args.text)
+            else:
+                data = synth.text_fragments(wave_units, FRAG, seed=0x5EED0003, device=dev, first=first)
+            _, ms_d, csum = codec_pass(data, unit, wave_units, wm, 0, 3, bufs)
+            checked += check_sample(data.view(wave_units, unit), unit, wm, bufs[0], bufs[1], bufs[5], k=32)
+            ms_sum, n_sum, c_sum = ms_sum + ms_d, n_sum + float(wave_units) * unit, c_sum + csum
+            del data
+        (ms_d,), (tot_n, tot_c) = reduce([ms_sum], [n_sum, c_sum])
+        alg_d = (tot_c + tot_n) / world + 8 * wave_units * waves
+        dec[name] = {"unit_bytes": unit, "wm": wm, "units_per_wave": wave_units, "waves": waves,
+                     "bytes_decoded_per_gpu": int(n_sum), "ratio": round(tot_c / tot_n, 4),
+                     "decompress_gbs": round(tot_n / ms_d / 1e6, 2), "decompress_ms_per_corpus": round(ms_d, 3),
+                     "roofline_frac_decompress": round(alg_d / ms_d / 1e6 / peak, 4),
+                     "units_checked_against_cpu_reference": checked,
+                     "note": "slot and output offsets of a wave exceed 2^32; every wave is checked by exact round trip"}
+        del bufs
+        torch.cuda.empty_cache()
+    out["decode_only"] = dec
+    return out
 
 
 def main():
@@ -187,6 +312,11 @@ def main():
                     help="text class (SURVEY.md 8d config 2): 4 KiB slices of the reference's urls.10K at seeded "
                          "offsets (default), or the purely synthetic alternative, a Zipf(1.1) word stream")
     ap.add_argument("--no-alt", action="store_true", help="skip the short run on the alternative text class")
+    ap.add_argument("--cpu-pages", type=int, default=0, help="--impl reference: bound the pages per step (0 = all --pages)")
+    ap.add_argument("--no-workloads", action="store_true", help="skip the fragments_32k / decode_only workloads")
+    ap.add_argument("--frag-gib", type=float, default=4.0, help="fragments_32k: GiB of 32 KiB fragments per GPU")
+    ap.add_argument("--decode-gib", type=float, default=64.0, help="decode_only: GiB of corpus per GPU and unit size")
+    ap.add_argument("--wave-gib", type=float, default=16.0, help="decode_only: GiB per wave")
     ap.add_argument("--only", default="", choices=["", "text", "zero", "random"],
                     help="diagnostic: make every page of one class (not the BASELINE workload)")
     args = ap.parse_args()
@@ -280,7 +410,7 @@ def main():
     # The call a block_compressor / zram style user makes: pages in host memory -> the page container
     # (block_compressor.c:275-345) in host memory, and back (block_compressor.c:347-394).  Every step
     # copies all pages H2D, the container D2H, the container H2D and all pages D2H inside the timed region.
-    e2e_ms = None
+    e2e_ms = e2e_pageable_ms = None
     h2d = d2h = 0
     if not args.no_e2e:
         h_in = torch.empty(B * PAGE, dtype=torch.uint8, pin_memory=True)
@@ -313,7 +443,20 @@ def main():
         payload = clen_box[0] - 4 - 4 * B
         h2d = B * PAGE + payload + 4 * B
         d2h = payload + 4 * B + 8 * ((B + 8191) // 8192) + B * PAGE + 8 * B
-        del h_in, h_cont, h_back
+        # the same calls on ordinary pageable caller memory (what a caller that never heard of CUDA passes in)
+        p_in, p_back = h_in.clone(memory_format=torch.contiguous_format), torch.empty(B * PAGE, dtype=torch.uint8)
+        p_cont = torch.empty(h_cont.numel(), dtype=torch.uint8)
+        assert not p_in.is_pinned() and not p_cont.is_pinned()
+        h_in, h_cont, h_back = p_in, p_cont, p_back
+        e2e_step()
+        assert torch.equal(h_back, h_in), "pageable e2e round trip mismatch"
+        barrier()
+        w0 = time.perf_counter()
+        for _ in range(2):
+            e2e_step()
+        torch.cuda.synchronize()
+        e2e_pageable_ms = 1e3 * (time.perf_counter() - w0) / 2
+        del h_in, h_cont, h_back, p_in, p_cont, p_back
 
     # ---- short diagnostic runs (device-resident, rank 0's times): the alternative text class of SURVEY 8d, and
     # ---- every page class of the main workload on its own ("report per-class and mixed") ----------
@@ -362,13 +505,25 @@ def main():
                                                      only=c), Bc) for c in ("text", "zero", "random")}
         del a_comp, a_back
 
+    # ---- BASELINE.json configs[2] and [3], device-resident, every rank ---------
+    workloads = None
+    S_cpu = min(B, 1 << 18)
+    host_sample = got_len_sample = None
+    if world == 1 and not args.no_cpu:
+        host_sample = pages.view(B, PAGE)[:S_cpu].cpu().numpy()
+        got_len_sample = comp_len[:S_cpu].cpu().numpy().astype(np.uint32)
+    if not args.no_workloads and not args.only:
+        del pages, comp, back
+        torch.cuda.empty_cache()
+        workloads = run_workloads(args, cs, synth, dev, rank, world, barrier)
+
     # ---- reduce over ranks: max time, sum bytes -------------------------------------------
-    vals = torch.tensor([elapsed_ms, tc_ms, td_ms, e2e_ms or 0.0], dtype=torch.float64, device=dev)
+    vals = torch.tensor([elapsed_ms, tc_ms, td_ms, e2e_ms or 0.0, e2e_pageable_ms or 0.0], dtype=torch.float64, device=dev)
     sums = torch.tensor([float(B * PAGE), float(csum), float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    elapsed_ms, tc_ms, td_ms, e2e_max = vals.tolist()
+    elapsed_ms, tc_ms, td_ms, e2e_max, e2e_pageable_max = vals.tolist()
     total_n, total_c, total_launches = sums.tolist()
 
     if rank == 0:
@@ -390,11 +545,7 @@ def main():
             "metric": METRIC, "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"zram-style batch: synthetic 4 KiB pages (50% text [{TEXT_DESC[args.text]}] / 25% zero / "
-                                   "25% random), wm 13, compress then decompress", "pages_per_gpu": B, "page_bytes": PAGE,
-                       "wm": WM, "ratio": round(total_c / total_n, 4), "parallelism": f"shard{world} (no collective)",
-                       "l2": "inputs (4 GiB per GPU) exceed the 126 MB L2; no explicit flush",
-                       "value_definition": "(bytes compressed + bytes decompressed) / step time"},
+            "config": workload_config(args.text, B, world, round(total_c / total_n, 4)),
             "compress_gbs": round(total_n / (tc_ms * 1e-3) / 1e9, 2),
             "decompress_gbs": round(total_n / (td_ms * 1e-3) / 1e9, 2),
             "roofline": {"kernel": f"{dominant}_kernel", "bound": "hbm",
@@ -421,24 +572,24 @@ def main():
                            "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
                            "ms_per_step": round(e2e_max, 2),
                            "api": "csnappy_bc_compress_host + csnappy_bc_decompress_host (block_compressor page container), pinned host buffers"}
-        if world == 1 and not args.no_cpu:
-            import oracle
-
-            impl = "reference" if oracle.have_reference() else "port"
-            cores = host_cores()
-            S = min(B, 1 << 18)
-            host = pages.view(B, PAGE)[:S].cpu().numpy()
-            tc, td, ref_out, ref_len = cpu_codec_pass(host, cores, impl)
-            t1c, _, _, _ = cpu_codec_pass(host[: S // 8], 1, impl, repeats=1)
+        if e2e_pageable_max:
+            line["e2e_pageable"] = {"value": round(2 * total_n / (e2e_pageable_max * 1e-3) / 1e9, 2), "unit": "GB/s",
+                                    "ms_per_step": round(e2e_pageable_max, 2),
+                                    "api": "the same two calls on pageable caller memory, mean of 2 steps after 1 warm-up"}
+        if workloads:
+            line["workloads"] = workloads
+        if host_sample is not None:
+            r, tc, td, impl, cores = cpu_measure(host_sample, WM, 1, 3)
+            r1 = __import__("oracle").BatchRunner(host_sample[: S_cpu // 8], WM, impl, threads=1)
+            t1c = r1.compress()
             # the same pass is the bulk parity check of what was timed
-            got_len = comp_len[:S].cpu().numpy().astype(np.uint32)
-            assert (got_len == ref_len).all(), "GPU compressed sizes differ from the CPU reference"
+            assert (got_len_sample == r.comp_len).all(), "GPU compressed sizes differ from the CPU reference"
             line["cpu_baseline"] = {
-                "value": round(2 * S * PAGE / (tc + td) / 1e9, 3), "unit": "GB/s", "cores": cores, "kind": impl,
-                "sample": f"first {S} pages ({S * PAGE >> 20} MiB) of the same batch, compress + decompress, "
-                          f"best of 3, {cores} pthreads",
-                "compress_gbs": round(S * PAGE / tc / 1e9, 3), "decompress_gbs": round(S * PAGE / td / 1e9, 3),
-                "single_thread_compress_gbs": round((S // 8) * PAGE / t1c / 1e9, 3)}
+                "value": round(2 * S_cpu * PAGE / (tc + td) / 1e9, 3), "unit": "GB/s", "cores": cores, "kind": impl,
+                "sample": f"first {S_cpu} pages ({S_cpu * PAGE >> 20} MiB) of the same batch, compress + decompress, "
+                          f"{cores} pthreads, static partition, mean of 3 steps after 1 warm-up",
+                "compress_gbs": round(S_cpu * PAGE / tc / 1e9, 3), "decompress_gbs": round(S_cpu * PAGE / td / 1e9, 3),
+                "single_thread_compress_gbs": round((S_cpu // 8) * PAGE / t1c / 1e9, 3)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

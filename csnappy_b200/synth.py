@@ -106,14 +106,21 @@ def mixed_pages(n_pages: int, page_len: int = 4096, seed: int = 0x5EED0001, devi
     return pages.view(-1)
 
 
+_POOLS: dict = {}
+
+
 def text_fragments(n_frag: int, frag_len: int = 32768, seed: int = 0x5EED0002, device="cuda", first: int = 0,
                    pool_bytes: int = 32 << 20):
-    """Config 3: text-like 32 KiB fragments (slices of the word stream at seeded offsets)."""
+    """Config 3: text-like 32 KiB fragments (slices of the word stream at seeded offsets; fragment i of the global
+    stream is the same whatever rank generates it: `first` is the rank's first fragment)."""
     import torch
 
     with np.errstate(over="ignore"):
         h = splitmix64(np.arange(first, first + n_frag, dtype=np.uint64) ^ np.uint64(seed))
-    pool = torch.from_numpy(text_pool(pool_bytes, seed)).to(device)
+    key = (pool_bytes, str(device))
+    if key not in _POOLS:  # the pool itself is fixed (seed 0x5EED0002); `seed` picks the offsets
+        _POOLS[key] = torch.from_numpy(text_pool(pool_bytes)).to(device)
+    pool = _POOLS[key]
     windows = pool.unfold(0, frag_len, 1)
     offs = torch.from_numpy((h % np.uint64(pool_bytes - frag_len)).astype(np.int64)).to(device)
     out = torch.empty((n_frag, frag_len), dtype=torch.uint8, device=device)

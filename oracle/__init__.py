@@ -234,3 +234,58 @@ def batch_decompress(comp: np.ndarray, comp_len: np.ndarray, cap: int, impl: str
     if sec < 0:
         raise RuntimeError("cpu harness failed")
     return out, out_len, status, sec
+
+
+class BatchRunner:
+    """compress + decompress one strided batch on the CPU, repeatedly, with buffers allocated and touched ONCE
+    (a fresh np.zeros per pass would put first-touch page faults of the output into every timed pass).
+    units: uint8 [B, unit_len].  The one CPU-baseline protocol of bench.py: `measure(warmup, steps)` = mean seconds
+    of `steps` passes after `warmup` passes, compress and decompress timed separately inside the C harness."""
+
+    def __init__(self, units: np.ndarray, wm: int, impl: str = "port", threads: int = 1):
+        assert units.dtype == np.uint8 and units.ndim == 2 and units.flags.c_contiguous
+        self.B, self.unit = units.shape
+        self.wm, self.threads, self.impl_id = wm, threads, _impl_id(impl)
+        self.units = units
+        # the reference's literal fast path reads up to 15 B past a short literal: pad the source
+        self.src = np.concatenate([units.reshape(-1), np.zeros(64, np.uint8)])
+        self.out_stride = (max_compressed_length(self.unit) + 15) // 16 * 16
+        self.comp = np.zeros(self.B * self.out_stride + 64, dtype=np.uint8)
+        self.comp_len = np.zeros(self.B, dtype=np.uint32)
+        self.back_stride = (self.unit + 64 + 15) // 16 * 16
+        self.back = np.zeros(self.B * self.back_stride, dtype=np.uint8)
+        self.back_len = np.zeros(self.B, dtype=np.uint32)
+        self.status = np.zeros(self.B, dtype=np.int32)
+        self.comp[::4096] = 1  # touch every page of the output buffers before anything is timed
+        self.back[::4096] = 1
+
+    def compress(self) -> float:
+        sec = port().L.harness_compress_pages(self.impl_id, self.src.ctypes.data, self.unit, None, self.unit, self.B,
+                                              self.comp.ctypes.data, self.out_stride, self.comp_len.ctypes.data,
+                                              self.wm, self.threads)
+        if sec < 0:
+            raise RuntimeError("cpu harness failed")
+        return sec
+
+    def decompress(self) -> float:
+        sec = port().L.harness_decompress_pages(self.impl_id, self.comp.ctypes.data, self.out_stride,
+                                                self.comp_len.ctypes.data, self.B, self.back.ctypes.data,
+                                                self.back_stride, self.unit, self.back_len.ctypes.data,
+                                                self.status.ctypes.data, self.threads)
+        if sec < 0:
+            raise RuntimeError("cpu harness failed")
+        return sec
+
+    def measure(self, warmup: int, steps: int):
+        """-> (mean compress seconds, mean decompress seconds) over `steps` passes; checks the round trip once."""
+        tc = td = 0.0
+        for it in range(warmup + steps):
+            c, d = self.compress(), self.decompress()
+            if it >= warmup:
+                tc, td = tc + c, td + d
+        back = self.back.reshape(self.B, self.back_stride)[:, : self.unit]
+        assert (self.status == 0).all() and (self.back_len == self.unit).all() and (back == self.units).all()
+        return tc / steps, td / steps
+
+    def compressed(self, i: int) -> bytes:
+        return self.comp[i * self.out_stride: i * self.out_stride + int(self.comp_len[i])].tobytes()

@@ -28,11 +28,15 @@ def test_reference_arm_line_on_cpu():
     assert d["cpu_baseline"]["cores"] >= 1 and "pages" in d["cpu_baseline"]["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"] and d["gpu_launches"] == 0
+    # the same config keys as the B200 arm prints (the driver compares the two dicts)
+    assert set(d["config"]) == {"workload", "pages_per_gpu", "page_bytes", "wm", "ratio", "parallelism", "l2", "value_definition"}
+    assert d["config"]["pages_per_gpu"] == 2048 and 0.3 < d["config"]["ratio"] < 0.7
 
 
 @pytest.mark.gpu
 def test_b200_arm_line_on_gpu():
-    d = run_bench("--pages", "32768", "--steps", "3", "--warmup", "3")
+    d = run_bench("--pages", "32768", "--steps", "3", "--warmup", "3", "--frag-gib", "0.0625", "--decode-gib", "0.25",
+                  "--wave-gib", "0.125")
     assert "impl" not in d and BASE_KEYS | {"roofline", "clocks", "compress_gbs", "decompress_gbs"} <= set(d)
     assert d["n_gpus"] == 1 and d["steps"] == 3 and d["warmup"] == 3 and d["scaling"] == "weak" and d["data"] == "synthetic"
     assert d["gpu_launches"] == 6  # one compress + one decompress kernel per step
@@ -42,6 +46,17 @@ def test_b200_arm_line_on_gpu():
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] > 32768 * 4096 and e["d2h_bytes_per_step"] > 32768 * 4096
     assert e["value"] < d["value"]  # host buffers and PCIe inside the timed region
+    assert 0 < d["e2e_pageable"]["value"] < d["value"]
+    # BASELINE.json configs[2] / [3] ride in the same line
+    w = d["workloads"]
+    for wm in ("wm15", "wm16"):
+        f = w["fragments_32k"][wm]
+        assert f["compress_gbs"] > 0 and f["decompress_gbs"] > 0 and 0 < f["roofline_frac_compress"] < 1
+        assert f["units_checked_against_cpu_reference"] > 0 and 0.4 < f["ratio"] < 0.6
+    for k in ("pages_4k", "fragments_32k"):
+        x = w["decode_only"][k]
+        assert x["waves"] == 2 and x["decompress_gbs"] > 0 and 0 < x["roofline_frac_decompress"] < 1
+        assert x["bytes_decoded_per_gpu"] == 2 * x["units_per_wave"] * x["unit_bytes"]
     c = d["cpu_baseline"]
     assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and c["value"] > 0
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
