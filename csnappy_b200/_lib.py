@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcsnappy_b200.so")
+LIB_PATH = os.environ.get("CSNAPPY_B200_LIB") or os.path.join(_HERE, "libcsnappy_b200.so")  # override: kernel experiments
 
 _lib = None
 

@@ -16,8 +16,9 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libcsnappy_b200.so")
+TAG = os.environ.get("CSB_BUILD_TAG", "")  # experiments: a variant library next to the product one (see CSNAPPY_B200_LIB)
+OBJ = os.path.join(HERE, "build" + ("_" + TAG if TAG else ""))
+LIB = os.path.join(HERE, "libcsnappy_b200" + ("_" + TAG if TAG else "") + ".so")
 CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
 NVCC = shutil.which("nvcc") or os.path.join(CUDA_HOME, "bin", "nvcc")
 

@@ -205,6 +205,26 @@ __device__ __forceinline__ uint32_t flush_tokens(const Group<G> &g, uint8_t *dst
 	return op;
 }
 
+// match extension, bounded by n (csnappy_compress.c:252-295): the first G bytes one byte per lane (most
+// copies end there), then 4*G bytes per step.  ip_a / cd_a: shared addresses of the two 4-byte-equal positions.
+template <int G>
+__device__ __forceinline__ uint32_t extend_match(const Group<G> &g, uint32_t ip_a, uint32_t cd_a, uint32_t room)
+{
+	const unsigned ne = g.ballot(lds_u8(cd_a + 4 + g.lane) != lds_u8(ip_a + 4 + g.lane) || 4 + g.lane >= room);
+	if (ne)
+		return 3 + __ffs(ne);
+	uint32_t m = 4 + G;
+	for (;;) {
+		const uint32_t d = min(m + 4 * g.lane, room);
+		const uint32_t x = lds32u_a(cd_a + d) ^ lds32u_a(ip_a + d);
+		uint32_t mk = x ? d + ((uint32_t)(__ffs(x) - 1) >> 3) : 0x7fffffffu;
+		mk = g.min(min(mk, room));
+		if (mk < m + 4 * G)
+			return mk;
+		m += 4 * G;
+	}
+}
+
 // ---- the kernel ------------------------------------------------------------------------------
 
 enum : int { ST_NEED = 0, ST_LOADING = 1, ST_RUN = 2 };
@@ -297,6 +317,84 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 			state = ST_RUN;
 		}
 
+		bool fin;
+		do {
+		fin = false;
+		// ---- fast path (G == 32): a window of 32 CONSECUTIVE positions in which no two lanes share a hash slot ----
+		// The common window of compressible data (3 of 4 windows on text): all strides are 1 (j0 <= 0: page start,
+		// or right behind a copy), so lane k probes wbase + k, ip = wbase + lane needs no shuffle, "all lanes valid"
+		// is a scalar test, and with every slot private to one lane the table entries read before the inserts ARE
+		// the candidates the serial code sees, however many copies the window holds.  The candidate bytes are
+		// loaded before the readback is evaluated (both depend only on `old`).  A shared slot (readback differs)
+		// restores the table and hands the window to the general code below.
+		bool done_fast = false;
+		if (G == 32 && j0 <= 0) {
+			const uint32_t pp = wbase + g.lane;
+			const bool valid = pp < ip_limit;
+			// invalid lanes read on inside the staging pad (pp + 3 <= n + 19) and never store
+			const uint32_t bytes = lds32u_a(sin_a + pp);
+			const uint32_t slot = tab_a + 2 * ((bytes * kHashMul) >> shift);
+			const uint32_t old = lds_u16(slot);
+			g.sync();
+			if (valid)
+				sts_u16(slot, pp);
+			g.sync();
+			const uint32_t rb1 = lds_u16(slot);
+			const uint32_t cand = valid ? old : 0u;  // (blocks under 15 bytes never clear the table)
+			const uint32_t cb = lds32u_a(sin_a + cand);
+			if (g.ballot(valid && rb1 != pp)) {
+				g.sync();  // every lane has read back before anybody restores
+				if (valid)
+					sts_u16(slot, old);
+				g.sync();
+			} else {
+				done_fast = true;
+				const unsigned H = g.ballot(valid && cb == bytes);
+				const bool all_valid = wbase + 31 < ip_limit;
+				uint32_t cur = t;
+				for (;;) {
+					const unsigned elig = H & (0xffffffffu << cur);
+					if (!elig) {
+						if (!all_valid) {
+							fin = true;  // ran into ip_limit without a hit
+						} else {
+							wbase += 32;
+							j0 += 32;
+							t = 0;
+						}
+						break;
+					}
+					const uint32_t f = __ffs(elig) - 1;
+					const uint32_t ip = wbase + f, cd = g.bcast(cand, (int)f);
+					const uint32_t m = extend_match<G>(g, sin_a + ip, sin_a + cd, n - ip);
+					sts_v2(tok_a + 8 * ntok, next_emit | (ip << 16), cd | (m << 16));
+					if (++ntok == kTokens) {
+						op = flush_tokens<G>(g, dst, op, sin_a, tok_a, ntok);
+						ntok = 0;
+					}
+					next_emit = ip + m;
+					if (next_emit >= ip_limit) {
+						fin = true;
+						break;
+					}
+					const uint32_t nl = next_emit - wbase;  // lane of the re-probe position
+					// lanes skipped by the copy never insert: undo (ip-1 = lane nl-1 stays, ip = lane nl goes on)
+					if (valid && g.lane > f && g.lane + 1 < nl)
+						sts_u16(slot, old);
+					if (nl >= 32u) {
+						wbase = next_emit - 1;
+						j0 = -2;
+						t = 1;
+						break;
+					}
+					cur = nl;
+					j0 = -(int)(nl + 1);
+				}
+				if (!fin)
+					g.sync();
+			}
+		}
+		if (!done_fast) {
 		// ---- one WINDOW of G probe positions (csnappy_compress.c:535-552 and 587-593) ----
 		// Lane k probes the k-th position of the window.  j0 + k is that probe's index in the
 		// reference's skip schedule (stride (32 + index) >> 5); lanes whose index is negative
@@ -371,7 +469,6 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 
 		uint32_t cur = t;      // first lane that may hit
 		unsigned fhit = 32;    // exact windows: the (single) hit lane
-		bool fin = false;
 		for (;;) {
 			const unsigned elig = H & (full << cur) & full;
 			if (!elig) {
@@ -392,29 +489,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 			}
 			const unsigned f = __ffs(elig) - 1;
 			const uint32_t ip = g.bcast(pp, (int)f), cd = g.bcast(cand, (int)f);
-			// match extension, bounded by n (csnappy_compress.c:252-295): the first G bytes one
-			// byte per lane (most copies end there), then 4*G bytes per step
-			const uint32_t room = n - ip;
-			const uint32_t ip_a = sin_a + ip, cd_a = sin_a + cd;
-			uint32_t m;
-			{
-				const unsigned ne = g.ballot(lds_u8(cd_a + 4 + g.lane) != lds_u8(ip_a + 4 + g.lane) || 4 + g.lane >= room);
-				m = 3 + __ffs(ne);
-				if (!ne) {
-					m = 4 + G;
-					for (;;) {
-						const uint32_t d = min(m + 4 * g.lane, room);
-						const uint32_t x = lds32u_a(cd_a + d) ^ lds32u_a(ip_a + d);
-						uint32_t mk = x ? d + ((uint32_t)(__ffs(x) - 1) >> 3) : 0x7fffffffu;
-						mk = g.min(min(mk, room));
-						if (mk < m + 4 * G) {
-							m = mk;
-							break;
-						}
-						m += 4 * G;
-					}
-				}
-			}
+			const uint32_t m = extend_match<G>(g, sin_a + ip, sin_a + cd, n - ip);
 			// record the match; emission is deferred (flush_tokens)
 			sts_v2(tok_a + 8 * ntok, next_emit | (ip << 16), cd | (m << 16));
 			if (++ntok == kTokens) {
@@ -455,7 +530,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 					sts_u16(slot, pp);
 			}
 			g.sync();
-		} else {
+		}
+		}  // general window
+		} while (G == 32 && !fin);  // one group per warp: stay in the window loop until the block is parsed
+		if (fin) {
 			if (ntok)
 				op = flush_tokens<G>(g, dst, op, sin_a, tok_a, ntok);
 			ntok = 0;

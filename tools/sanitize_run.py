@@ -30,6 +30,16 @@ for lanes in (32, 16, 8):
     back2, _, st2 = cs.batch_decompress(packed, out_len, B, L, in_off=off[:-1].contiguous())
     torch.cuda.synchronize()
     assert int((st2 != 0).sum()) == 0 and torch.equal(back2.view(B, L), pages.view(B, L)), lanes
+# the other decoder families on the same batch: 3 = warp per block against global memory, 4 = lane per block
+cs.set_tuning("compress_lanes", 0)
+cs.set_tuning("decompress_lanes", 0)
+out, out_len = cs.batch_compress_fragments(pages, L, B, 13)
+for stage in (3, 4, 2, 1):
+    cs.set_tuning("decompress_stage_input", stage)
+    back, back_len, status = cs.batch_decompress(out, out_len, B, L, in_stride=cs.api.out_stride_for(L))
+    torch.cuda.synchronize()
+    assert int((status != 0).sum()) == 0 and torch.equal(back.view(B, L), pages.view(B, L)), stage
+cs.set_tuning("decompress_stage_input", 0)
 # 32 KiB fragments
 frag = synth.text_fragments(6, 32768, device="cuda", pool_bytes=1 << 20)
 o, ol = cs.batch_compress_fragments(frag, 32768, 6, 15)
@@ -39,7 +49,7 @@ assert int((st != 0).sum()) == 0 and torch.equal(b.view(6, 32768), frag.view(6, 
 # whole multi-chunk streams through the drop-in API (global decode path) and the page container
 import gzip
 
-urls = gzip.open("tests/golden/urls.10K.gz").read()[:200000]
+urls = gzip.open("csnappy_b200/data/urls.10K.gz").read()[:200000]
 c = cs.csnappy_compress(urls, 15)
 rc, outb = cs.csnappy_decompress(c, len(urls))
 assert rc == 0 and outb == urls

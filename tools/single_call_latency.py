@@ -8,7 +8,7 @@ import gzip
 
 import csnappy_b200 as cs
 
-page = gzip.open("tests/golden/urls.10K.gz").read()[:4096]
+page = gzip.open("csnappy_b200/data/urls.10K.gz").read()[:4096]
 comp = cs.csnappy_compress_fragment(page, 13)
 for name, fn in (("csnappy_compress_fragment(4 KiB)", lambda: cs.csnappy_compress_fragment(page, 13)),
                  ("csnappy_decompress_noheader(4 KiB)", lambda: cs.csnappy_decompress_noheader(comp, 4096))):
