@@ -320,17 +320,22 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 		bool fin;
 		do {
 		fin = false;
-		// ---- fast path (G == 32): a window of 32 CONSECUTIVE positions in which no two lanes share a hash slot ----
-		// The common window of compressible data (3 of 4 windows on text): all strides are 1 (j0 <= 0: page start,
-		// or right behind a copy), so lane k probes wbase + k, ip = wbase + lane needs no shuffle, "all lanes valid"
-		// is a scalar test, and with every slot private to one lane the table entries read before the inserts ARE
-		// the candidates the serial code sees, however many copies the window holds.  The candidate bytes are
-		// loaded before the readback is evaluated (both depend only on `old`).  A shared slot (readback differs)
-		// restores the table and hands the window to the general code below.
+		// ---- fast path (G == 32): a window of CONSECUTIVE positions in which no two lanes share a hash slot ----
+		// The common window of compressible data: lanes 0..cut-1 probe wbase + lane with stride 1 (probe indices
+		// j0 + lane <= 31: page start, right behind a copy, or the stride-1 head of a later window), so
+		// ip = wbase + lane needs no shuffle, "all lanes valid" is a scalar test, and with every slot private to one
+		// lane the table entries read before the inserts ARE the candidates the serial code sees, however many
+		// copies the window holds.  The candidate bytes are loaded before the readback is evaluated (both depend
+		// only on `old`).  Two lanes on one slot (a third of the windows on URL text: repeated 4-byte groups) are
+		// told apart by a second insert + readback -- after it each lane of a pair knows its partner's position --
+		// and the window is CUT in front of the first lane that has a lower partner: the lanes before it are
+		// conflict-free, the lanes from it on take their inserts back and are probed again by the next window.
+		// Three or more lanes on one slot restore the table and hand the window to the general code below.
 		bool done_fast = false;
-		if (G == 32 && j0 <= 0) {
+		if (G == 32 && j0 < 24) {
+			uint32_t cut = j0 > 0 ? 32u - (uint32_t)j0 : 32u;
 			const uint32_t pp = wbase + g.lane;
-			const bool valid = pp < ip_limit;
+			bool valid = pp < ip_limit && g.lane < cut;
 			// invalid lanes read on inside the staging pad (pp + 3 <= n + 19) and never store
 			const uint32_t bytes = lds32u_a(sin_a + pp);
 			const uint32_t slot = tab_a + 2 * ((bytes * kHashMul) >> shift);
@@ -342,15 +347,39 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 			const uint32_t rb1 = lds_u16(slot);
 			const uint32_t cand = valid ? old : 0u;  // (blocks under 15 bytes never clear the table)
 			const uint32_t cb = lds32u_a(sin_a + cand);
-			if (g.ballot(valid && rb1 != pp)) {
-				g.sync();  // every lane has read back before anybody restores
-				if (valid)
-					sts_u16(slot, old);
+			const bool lost = valid && rb1 != pp;
+			done_fast = true;
+			if (g.ballot(lost)) {
 				g.sync();
-			} else {
-				done_fast = true;
+				if (lost)
+					sts_u16(slot, pp);
+				g.sync();
+				const uint32_t rb2 = lds_u16(slot);
+				const bool triple = g.ballot(lost && rb2 != pp) != 0;
+				g.sync();  // every lane has read back before anybody rewrites
+				if (triple) {
+					if (valid)
+						sts_u16(slot, old);
+					done_fast = false;
+				} else {
+					const uint32_t q = lost ? rb1 : rb2;  // the partner's position (own position: none)
+					const bool hasp = valid && q != pp;
+					const uint32_t pl = q - wbase;
+					cut = __ffs(g.ballot(hasp && q < pp)) - 1;  // first lane with a lower partner (there is one)
+					const bool upper = g.lane >= cut;
+					// lanes from the cut on leave the table as if they had never inserted; a lane in front of the
+					// cut whose partner is behind it owns the slot again
+					const bool wr_old = valid && upper && (!hasp || (pl >= cut && g.lane < pl));
+					const bool wr_pp = valid && !upper && hasp;
+					if (wr_old || wr_pp)
+						sts_u16(slot, wr_pp ? pp : old);
+					valid = valid && !upper;
+				}
+				g.sync();
+			}
+			if (done_fast) {
 				const unsigned H = g.ballot(valid && cb == bytes);
-				const bool all_valid = wbase + 31 < ip_limit;
+				const bool all_valid = wbase + cut - 1 < ip_limit;
 				uint32_t cur = t;
 				for (;;) {
 					const unsigned elig = H & (0xffffffffu << cur);
@@ -358,8 +387,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 						if (!all_valid) {
 							fin = true;  // ran into ip_limit without a hit
 						} else {
-							wbase += 32;
-							j0 += 32;
+							wbase += cut;
+							j0 += (int)cut;
 							t = 0;
 						}
 						break;
@@ -381,7 +410,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 					// lanes skipped by the copy never insert: undo (ip-1 = lane nl-1 stays, ip = lane nl goes on)
 					if (valid && g.lane > f && g.lane + 1 < nl)
 						sts_u16(slot, old);
-					if (nl >= 32u) {
+					if (nl >= cut) {
 						wbase = next_emit - 1;
 						j0 = -2;
 						t = 1;

@@ -65,7 +65,7 @@ int csnappy_b200_device_ok(void) { return csnappy_b200_device_count() > 0; }
 uint64_t csnappy_b200_kernel_launches(void) { return csb_launch_count(); }
 
 /* ---- tuning knobs ------------------------------------------------------- */
-static int g_compress_lanes, g_decompress_lanes, g_ctas_per_sm, g_stage_input, g_smem_kb, g_host_register, g_stream_min;
+static int g_compress_lanes, g_decompress_lanes, g_ctas_per_sm, g_stage_input, g_smem_kb, g_host_register, g_stream_min, g_lane_warps;
 
 int csnappy_b200_set_tuning(const char *key, int value)
 {
@@ -90,6 +90,12 @@ int csnappy_b200_set_tuning(const char *key, int value)
 		if (value < 0 || value > 227)
 			return CSNAPPY_E_BAD_ARG;
 		g_smem_kb = value;
+		return 0;
+	}
+	if (!strcmp(key, "decompress_lane_warps")) { /* blocks in flight per SM of the lane-per-block decoder, in warps of 32 */
+		if (value < 0 || value > 64)
+			return CSNAPPY_E_BAD_ARG;
+		g_lane_warps = value;
 		return 0;
 	}
 	if (!strcmp(key, "ctas_per_sm")) {
@@ -156,6 +162,7 @@ static void fill_decompress_args(struct csb_decompress_args *a)
 	a->stage_input = g_stage_input;
 	a->smem_kb = g_smem_kb;
 	a->ctas_per_sm = g_ctas_per_sm;
+	a->lane_warps = g_lane_warps;
 }
 
 /* ---- batched device-pointer entry points -------------------------------- */
@@ -552,10 +559,12 @@ struct hostreg {
 };
 static void hostreg_begin(struct hostreg *r, const void *p, size_t n)
 {
+	/* the pages that CONTAIN the buffer (they are mapped: they hold its bytes); a copy that starts in an
+	 * unregistered head of a partly registered range is refused by the driver */
 	const size_t pg = (size_t)sysconf(_SC_PAGESIZE);
-	uintptr_t a = ((uintptr_t)p + pg - 1) & ~(uintptr_t)(pg - 1), b = ((uintptr_t)p + n) & ~(uintptr_t)(pg - 1);
+	uintptr_t a = (uintptr_t)p & ~(uintptr_t)(pg - 1), b = ((uintptr_t)p + n + pg - 1) & ~(uintptr_t)(pg - 1);
 	r->p = NULL;
-	if (!g_host_register || !p || b <= a || b - a < (8u << 20))
+	if (!g_host_register || !p || n < (8u << 20))
 		return;
 	if (cudaHostRegister((void *)a, b - a, cudaHostRegisterPortable) == cudaSuccess)
 		r->p = (void *)a;

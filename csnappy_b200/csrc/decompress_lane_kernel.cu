@@ -35,6 +35,7 @@ namespace csb {
 
 constexpr int L_OK = 0, L_HEADER_BAD = -1, L_OUTPUT_INSUF = -2, L_OUTPUT_OVERRUN = -3, L_DATA_MALFORMED = -5;
 constexpr int kLaneThreads = 256;
+constexpr int kLaneWarpsDefault = 32;
 constexpr uint32_t kBulkMin = 528;  // literals at least this long leave the lane loop for a warp-wide copy
 
 struct U128 {
@@ -91,6 +92,74 @@ __device__ __forceinline__ U128 load16(uintptr_t a, uint32_t need, uintptr_t lim
 	return r;
 }
 
+// ---- per-lane input ring in shared memory ------------------------------------------------------------
+// Every lane reads its own compressed block strictly forwards, 1..21 bytes per step.  Through L1 / L2 that is a
+// dependent long-latency load per tag on a cache thousands of lanes compete for (measured: the tag load alone was
+// 26-31 % of all stall samples, DRAM reads 5-7x the input).  Instead each lane owns a small ring of 64-byte lines
+// -- global byte address g lives at ring + (g & (kRing - 1)) -- and fetches ahead with cp.async (LDGSTS, 16 bytes
+// x 4, L2 only), so every input byte crosses L2 once and the tag / literal loads become LDS.  One step reads at
+// most 36 bytes ahead of its start (5 header + 16 payload bytes through two aligned 16-byte vectors), i.e. the
+// line of the read position and the next one.
+//   kRing 128 (default): two lines.  Entering a line requests the next one; the step that enters a line is at most
+//       20 bytes into it and cannot reach the next, so the request has a whole step to land: the loop waits for
+//       all cp.async groups but the newest.  16 KiB per 128-lane CTA: up to 52 warps per SM.
+//   kRing 256: four lines, three requested ahead, the loop waits for all but the two newest groups.  More slack,
+//       but only 24 warps per SM fit (measured: 405 vs 462 GB/s on URL text pages).
+#ifndef CSB_LANE_RING
+#define CSB_LANE_RING 128
+#endif
+constexpr uint32_t kRing = CSB_LANE_RING, kLine = 64, kAhead = kRing / kLine - 1;
+
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, uintptr_t gsrc)
+{
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void ring_fetch(uint32_t ring, uintptr_t line)
+{
+	const uint32_t d = ring + ((uint32_t)line & (kRing - 1));
+#pragma unroll
+	for (uint32_t i = 0; i < kLine; i += 16)
+		cp_async16(d + i, line + i);
+}
+// Keep the ring's invariant for read position g: the line holding g and the kAhead behind it are requested (lines
+// that start at or past `lim` hold no input byte and are never touched).  `have` = line of the previous read
+// position.  Returns true after a jump (new block, bulk literal): those lines are needed at once.
+__device__ __forceinline__ bool ring_ensure(uint32_t ring, uintptr_t g, uintptr_t lim, uintptr_t &have)
+{
+	const uintptr_t cur = g & ~(uintptr_t)(kLine - 1);
+	if (cur == have || cur >= lim)
+		return false;
+	const bool jump = cur != have + kLine;
+	have = cur;
+	if (jump) {
+#pragma unroll
+		for (uint32_t i = 0; i < kAhead; ++i)
+			if (cur + i * kLine < lim)
+				ring_fetch(ring, cur + i * kLine);
+	}
+	if (cur + kAhead * kLine < lim)
+		ring_fetch(ring, cur + kAhead * kLine);
+	return jump;
+}
+// `need` (1..16) bytes at global byte address g out of the ring, little endian
+__device__ __forceinline__ U128 ring_load16(uint32_t ring, uintptr_t g, uint32_t need)
+{
+	const uint32_t w = (uint32_t)g & ~15u, k = (uint32_t)g & 15u;
+	const uint4 a = lds_v4(ring + (w & (kRing - 1)));
+	uint4 b = make_uint4(0, 0, 0, 0);
+	if (k + need > 16)
+		b = lds_v4(ring + ((w + 16) & (kRing - 1)));
+	const uint64_t alo = ((uint64_t)a.y << 32) | a.x, ahi = ((uint64_t)a.w << 32) | a.z;
+	const uint64_t blo = ((uint64_t)b.y << 32) | b.x, bhi = ((uint64_t)b.w << 32) | b.z;
+	const bool q = k >= 8;
+	const uint32_t s = k & 7u;
+	const uint64_t x0 = q ? ahi : alo, x1 = q ? blo : ahi, x2 = q ? bhi : blo;
+	U128 r;
+	r.lo = shr_pair(x0, x1, s);
+	r.hi = shr_pair(x1, x2, s);
+	return r;
+}
+
 struct LaneParams {
 	csb_decompress_args a;
 	uint32_t *counter;
@@ -121,6 +190,10 @@ __global__ void __launch_bounds__(kLaneThreads) decompress_lane_kernel(const Lan
 	uint32_t blk = 0, cap = 0, ip = 0, op = 0, rem = 0, mode = M_LIT, off = 0;
 	uintptr_t src = 0, src_end = 0, dst = 0;
 	uint64_t acc0 = 0, acc1 = 0, pat = 0;  // acc: bytes [op & ~15, op) of the output, not yet stored
+	extern __shared__ __align__(128) uint8_t lane_smem[];
+	const uint32_t ring = smem_u32(lane_smem) + threadIdx.x * kRing;
+	uintptr_t have_line = 1;  // never a line address
+	bool fresh = false;       // lines were requested that the next step needs
 
 	for (;;) {
 		// ---- CLAIM ----
@@ -167,8 +240,22 @@ __global__ void __launch_bounds__(kLaneThreads) decompress_lane_kernel(const Lan
 					mode = M_LIT;
 					if ((a.flags & 4u) && ilen == cap)
 						rem = ilen;  // stored block (block_compressor.c:378): the whole input is one literal payload
+					have_line = 1;
 				}
 			}
+		}
+		// ---- INPUT RING: request what the new read position needs; wait for what this step reads ----
+		if (have)
+			fresh |= ring_ensure(ring, src + ip, src_end, have_line);
+		asm volatile("cp.async.commit_group;" ::: "memory");
+		if (__any_sync(full, fresh)) {
+			asm volatile("cp.async.wait_group 0;" ::: "memory");
+			fresh = false;
+		} else {
+			if (kAhead >= 3)
+				asm volatile("cp.async.wait_group 2;" ::: "memory");
+			else
+				asm volatile("cp.async.wait_group 1;" ::: "memory");
 		}
 		__syncwarp(full);
 		if (!__any_sync(full, have || more))
@@ -181,7 +268,7 @@ __global__ void __launch_bounds__(kLaneThreads) decompress_lane_kernel(const Lan
 			const bool fin = ip >= ilen;  // end of input at a tag boundary
 			if (!fin) {
 				const uint32_t left = ilen - ip;
-				const uint64_t x = load16(src + ip, left < 8 ? left : 8u, src_end).lo;
+				const uint64_t x = ring_load16(ring, src + ip, 8u).lo;  // bytes past the end are never used (hdr <= left)
 				const uint32_t tag = (uint32_t)x & 0xffu, kind = tag & 3u, lf = tag >> 2;
 				const uint32_t extra = (uint32_t)(x >> 8);
 				const bool lit = kind == 0, longlit = lit && lf >= 60;
@@ -226,6 +313,7 @@ __global__ void __launch_bounds__(kLaneThreads) decompress_lane_kernel(const Lan
 
 		// ---- BULK: a long literal (incompressible data, stored blocks) is copied by the whole warp ----
 		// once the owner's output position is 16-byte aligned (the MOVE phase below aligns it first)
+		bool moved = false;
 		unsigned bulk = __ballot_sync(full, have && mode == M_LIT && rem >= kBulkMin && (op & 15u) == 0);
 		while (bulk) {
 			const int o = __ffs(bulk) - 1;
@@ -242,12 +330,13 @@ __global__ void __launch_bounds__(kLaneThreads) decompress_lane_kernel(const Lan
 				ip += n_;
 				op += n_;
 				rem -= n_;
+				moved = true;  // the ring does not hold the new read position yet
 			}
 		}
 		__syncwarp(full);
 
 		// ---- MOVE: up to 16 bytes of the current tag ----
-		if (have && rem) {
+		if (have && rem && !moved) {
 			uint32_t n = rem < 16 ? rem : 16;
 			if (mode == M_LIT && rem >= kBulkMin)
 				n = 16 - (op & 15u);  // align the output for the bulk copy (16 when it already is: never here)
@@ -260,11 +349,11 @@ __global__ void __launch_bounds__(kLaneThreads) decompress_lane_kernel(const Lan
 					n = off;
 				flush_partial(dst, cap, op, acc0, acc1);
 			}
-			if (mode != M_PATTERN) {
-				const bool lit = mode == M_LIT;
-				v = load16(lit ? src + ip : dst + op - off, n, lit ? src_end : dst + cap);
-				if (lit)
-					ip += n;
+			if (mode == M_LIT) {
+				v = ring_load16(ring, src + ip, n);
+				ip += n;
+			} else if (mode != M_PATTERN) {
+				v = load16(dst + op - off, n, dst + cap);
 			}
 			// append the n low bytes of v (op + n <= cap was checked with the tag)
 			if (n < 16) {
@@ -319,11 +408,32 @@ extern "C" int csb_launch_decompress_lane(const struct csb_decompress_args *a, c
 	if (ce != cudaSuccess)
 		return (int)ce;
 	p.counter = counter;
-	long ctas = ((long)a->n_blocks + kLaneThreads - 1) / kLaneThreads;
-	const long max_ctas = (long)di.sm_count * (a->ctas_per_sm > 0 ? a->ctas_per_sm : 5);  // persistent: lanes claim blocks until none is left
+	// Persistent: lanes claim blocks until none is left.  Blocks in flight per SM = 32 * warps: more lanes hide more
+	// latency, but every lane's output page competes for L2, where the back-references read it back (measured on
+	// 4 KiB text pages, 1 Mi blocks: 16 warps 324, 24 warps 430, 32 warps 462, 48 warps 461 GB/s; 32 KiB fragments,
+	// 512 Ki blocks: 16 warps 226, 24 warps 273, 32 warps 282).
+	int warps = a->lane_warps > 0 ? a->lane_warps : (a->ctas_per_sm > 0 ? 8 * a->ctas_per_sm : kLaneWarpsDefault);
+	if (a->lane_warps <= 0 && a->ctas_per_sm <= 0) {
+		// a batch that fits the machine in ONE round of at most 40 warps per SM runs as one round: no second-round tail
+		const long need = ((long)a->n_blocks + 32L * di.sm_count - 1) / (32L * di.sm_count);
+		if (need > warps && need <= 40)
+			warps = (int)need;
+	}
+	const int threads = 128;  // 4 warps per CTA: fine granularity for the warps-per-SM knob
+	long ctas = ((long)a->n_blocks + threads - 1) / threads;
+	const long max_ctas = ((long)di.sm_count * warps + 3) / 4;
 	if (ctas > max_ctas)
 		ctas = max_ctas;
-	decompress_lane_kernel<<<(int)ctas, kLaneThreads, 0, s>>>(p);
+	const size_t smem = (size_t)threads * kRing;
+	const int fit = (int)((di.smem_per_sm / (smem + 1024)) * (threads / 32));  // warps per SM the rings leave room for
+	if (warps > fit) {
+		warps = fit;
+		ctas = ((long)a->n_blocks + threads - 1) / threads;
+		const long mc = ((long)di.sm_count * warps + 3) / 4;
+		if (ctas > mc)
+			ctas = mc;
+	}
+	decompress_lane_kernel<<<(int)ctas, threads, smem, s>>>(p);
 	count_launch();
 	return (int)cudaGetLastError();
 }

@@ -56,6 +56,7 @@ struct csb_decompress_args {
 	int stage_input;	/* 0: choose; 1: always stage in shared memory; 2: stage only the output; 3: warp per block against
 				   global memory; 4: one lane per block (decompress_lane_kernel.cu) */
 	int smem_kb;		/* unstaged mode: shared memory to use per SM, rest stays L1 (0 = default) */
+	int lane_warps;		/* lane-per-block decoder: warps (of 32 blocks) in flight per SM (0 = default) */
 };
 
 /* all return 0 or a cudaError_t value (> 0) */
