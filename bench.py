@@ -410,7 +410,7 @@ def main():
     # The call a block_compressor / zram style user makes: pages in host memory -> the page container
     # (block_compressor.c:275-345) in host memory, and back (block_compressor.c:347-394).  Every step
     # copies all pages H2D, the container D2H, the container H2D and all pages D2H inside the timed region.
-    e2e_ms = e2e_pageable_ms = e2e_registered_ms = None
+    e2e_ms = e2e_pageable_ms = None
     h2d = d2h = 0
     if not args.no_e2e:
         h_in = torch.empty(B * PAGE, dtype=torch.uint8, pin_memory=True)
@@ -456,18 +456,6 @@ def main():
             e2e_step()
         torch.cuda.synchronize()
         e2e_pageable_ms = 1e3 * (time.perf_counter() - w0) / 2
-        # ... and with the library page-locking the caller's buffers for the duration of each call
-        # (csnappy_b200_set_tuning("host_register", 1): cudaHostRegister + cudaHostUnregister inside every call)
-        cs.set_tuning("host_register", 1)
-        e2e_step()
-        barrier()
-        w0 = time.perf_counter()
-        for _ in range(2):
-            e2e_step()
-        torch.cuda.synchronize()
-        e2e_registered_ms = 1e3 * (time.perf_counter() - w0) / 2
-        cs.set_tuning("host_register", 0)
-        assert torch.equal(h_back, h_in), "pageable (registered) e2e round trip mismatch"
         del h_in, h_cont, h_back, p_in, p_cont, p_back
 
     # ---- short diagnostic runs (device-resident, rank 0's times): the alternative text class of SURVEY 8d, and
@@ -530,12 +518,12 @@ def main():
         workloads = run_workloads(args, cs, synth, dev, rank, world, barrier)
 
     # ---- reduce over ranks: max time, sum bytes -------------------------------------------
-    vals = torch.tensor([elapsed_ms, tc_ms, td_ms, e2e_ms or 0.0, e2e_pageable_ms or 0.0, e2e_registered_ms or 0.0], dtype=torch.float64, device=dev)
+    vals = torch.tensor([elapsed_ms, tc_ms, td_ms, e2e_ms or 0.0, e2e_pageable_ms or 0.0], dtype=torch.float64, device=dev)
     sums = torch.tensor([float(B * PAGE), float(csum), float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    elapsed_ms, tc_ms, td_ms, e2e_max, e2e_pageable_max, e2e_registered_max = vals.tolist()
+    elapsed_ms, tc_ms, td_ms, e2e_max, e2e_pageable_max = vals.tolist()
     total_n, total_c, total_launches = sums.tolist()
 
     if rank == 0:
@@ -587,11 +575,8 @@ def main():
         if e2e_pageable_max:
             line["e2e_pageable"] = {"value": round(2 * total_n / (e2e_pageable_max * 1e-3) / 1e9, 2), "unit": "GB/s",
                                     "ms_per_step": round(e2e_pageable_max, 2),
-                                    "api": "the same two calls on pageable caller memory, mean of 2 steps after 1 warm-up"}
-            if e2e_registered_max:
-                line["e2e_pageable"]["with_host_register"] = {
-                    "value": round(2 * total_n / (e2e_registered_max * 1e-3) / 1e9, 2), "ms_per_step": round(e2e_registered_max, 2),
-                    "note": "tuning host_register=1: the library page-locks the caller's buffers inside every call"}
+                                    "api": "the same two calls on pageable caller memory (chunks staged through pinned slot buffers by the "
+                                           "library's copy threads), mean of 2 steps after 1 warm-up"}
         if workloads:
             line["workloads"] = workloads
         if host_sample is not None:
