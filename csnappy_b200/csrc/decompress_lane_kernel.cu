@@ -382,6 +382,20 @@ __global__ void __launch_bounds__(kLaneThreads) decompress_lane_kernel(const Lan
 			}
 			op += n;
 			rem -= n;
+			// A pattern run (offset 1, 2, 4, 8: zero pages, RLE) repeats every 16 bytes: once a full 16-byte move
+			// has gone through the accumulator, every further vector of the run is the same value -- the k bytes
+			// left over plus the first 16 - k bytes of the pattern -- and the accumulator does not change.
+			if (mode == M_PATTERN && n == 16 && rem >= 16) {
+				const uint64_t v0 = acc0 | (q ? 0ull : t0), v1 = acc1 | (q ? t0 : t1);
+				uint32_t more = rem >> 4;
+				if (more > 15)
+					more = 15;
+				const uintptr_t at = dst + (op & ~15u);  // the last of these vectors ends at or below op + rem <= cap
+				for (uint32_t e = 0; e < more; ++e)
+					stg128(at + 16 * e, v0, v1);
+				op += 16 * more;
+				rem -= 16 * more;
+			}
 		}
 		__syncwarp(full);
 	}
