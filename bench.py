@@ -500,7 +500,7 @@ def main():
         other = "words" if args.text == "urls" else "urls"
         alt = {"text": TEXT_DESC[other], "note": "rank 0's times, mean of 3 steps after 3 warm-ups",
                **short_run(synth.mixed_pages(Ba, PAGE, seed=SEED, device=dev, first_page=first, text=other), Ba)}
-        Bc = min(B, 1 << 16)
+        Bc = min(B, 1 << 18)  # enough pages for the default decoder routing of a large batch (lane per page)
         per_class = {c: short_run(synth.mixed_pages(Bc, PAGE, seed=SEED, device=dev, first_page=first, text=args.text,
                                                      only=c), Bc) for c in ("text", "zero", "random")}
         del a_comp, a_back
