@@ -26,6 +26,8 @@
 //     (L2 merges them; the kernel is nowhere near the HBM roofline);
 //   * the per-group control flow is a flat state machine (claim / wait for the bulk copy /
 //     step), so the groups sharing a warp never wait for each other at block boundaries.
+#include <stdlib.h>
+
 #include "device_common.cuh"
 #include "kernels.h"
 
@@ -46,14 +48,60 @@ struct CompressParams {
 	uint32_t groups;       // groups per CTA that own shared memory
 };
 
+// ---- where a block's bytes are read from ---------------------------------------------------------
+// STAGED: the copy in shared memory (4 KiB pages: table + page = 12.6 KB, 18 pages per SM).  Not STAGED: global
+// memory through L1 / L2 (ld.global.nc) -- for fragments of which the staged form fits only 2-3 times per SM
+// (32 KiB + a 32 KiB table): with only the table in shared memory 7 chains run per SM, each a little slower
+// (the candidate load is an L2 round trip).  Both forms tolerate positions at or past the end of the block:
+// staged reads land in the staging pad, unstaged reads are clamped to the last word / byte of the block; either
+// way bytes at or past n are unspecified and every caller masks them (min(..., room)).
+template <bool STAGED>
+struct Input;
+template <>
+struct Input<true> {
+	uint32_t a;  // shared address of byte 0
+	__device__ __forceinline__ uint32_t u32(uint32_t pos) const { return lds32u_a(a + pos); }
+	__device__ __forceinline__ uint32_t u8(uint32_t pos) const { return lds_u8(a + pos); }
+};
+template <>
+struct Input<false> {
+	const uint8_t *base;   // byte 0
+	const uint8_t *base4;  // base rounded down to a 4-byte boundary
+	uint32_t boff, wlast, blast;  // base - base4; offset from base4 of the last word holding a block byte; n - 1
+	__device__ __forceinline__ void set(const uint8_t *src, uint32_t n)
+	{
+		base = src;
+		boff = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
+		base4 = src - boff;
+		blast = n ? n - 1 : 0;
+		wlast = (boff + blast) & ~3u;
+	}
+	static __device__ __forceinline__ uint32_t ldg32(const uint8_t *p)
+	{
+		uint32_t v;
+		asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+		return v;
+	}
+	__device__ __forceinline__ uint32_t u32(uint32_t pos) const
+	{
+		const uint32_t o = boff + pos, w0 = min(o & ~3u, wlast), w1 = min(w0 + 4u, wlast);
+		return __funnelshift_r(ldg32(base4 + w0), ldg32(base4 + w1), (o & 3u) * 8u);
+	}
+	__device__ __forceinline__ uint32_t u8(uint32_t pos) const
+	{
+		uint32_t v;
+		asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(base + min(pos, blast)) : "memory");
+		return v;
+	}
+};
+
 // ---- output: lane-parallel byte stores into the block's HBM slot ----------------------------
 
 // literal tag + payload, csnappy_compress.c:332-371.  Returns bytes written.
-template <int G>
-__device__ __forceinline__ uint32_t emit_literal(const Group<G> &g, uint8_t *dst, uint32_t sin_a, uint32_t src,
+template <int G, bool ST>
+__device__ __forceinline__ uint32_t emit_literal(const Group<G> &g, uint8_t *dst, const Input<ST> &in, uint32_t src,
 						 uint32_t len)
 {
-	src += sin_a;  // shared byte address of the payload
 	const uint32_t v = len - 1;
 	uint32_t hb, hdr;
 	if (v < 60) {
@@ -70,7 +118,7 @@ __device__ __forceinline__ uint32_t emit_literal(const Group<G> &g, uint8_t *dst
 	if (total <= (uint32_t)G) {
 		// common case: header and payload in one store
 		if (g.lane < total)
-			dst[g.lane] = g.lane < hb ? (uint8_t)(hdr >> (8 * g.lane)) : (uint8_t)lds_u8(src + g.lane - hb);
+			dst[g.lane] = g.lane < hb ? (uint8_t)(hdr >> (8 * g.lane)) : (uint8_t)in.u8(src + g.lane - hb);
 		return total;
 	}
 	if (g.lane < hb)
@@ -78,19 +126,19 @@ __device__ __forceinline__ uint32_t emit_literal(const Group<G> &g, uint8_t *dst
 	dst += hb;
 	if (len <= 4u * G) {
 		for (uint32_t i = g.lane; i < len; i += G)
-			dst[i] = (uint8_t)lds_u8(src + i);
+			dst[i] = (uint8_t)in.u8(src + i);
 	} else {
 		// word stores: head bytes up to a 4-byte aligned destination, realigned source words, tail
 		const uint32_t head = (uint32_t)(-(intptr_t)dst) & 3u;
 		if (g.lane < head)
-			dst[g.lane] = (uint8_t)lds_u8(src + g.lane);
+			dst[g.lane] = (uint8_t)in.u8(src + g.lane);
 		const uint32_t words = (len - head) >> 2;
 		uint32_t *dw = reinterpret_cast<uint32_t *>(dst + head);
 		for (uint32_t w = g.lane; w < words; w += G)
-			dw[w] = lds32u_a(src + head + 4 * w);
+			dw[w] = in.u32(src + head + 4 * w);
 		const uint32_t tail = head + (words << 2);
 		if (tail + g.lane < len)
-			dst[tail + g.lane] = (uint8_t)lds_u8(src + tail + g.lane);
+			dst[tail + g.lane] = (uint8_t)in.u8(src + tail + g.lane);
 	}
 	return total;
 }
@@ -140,8 +188,8 @@ __device__ __forceinline__ uint32_t emit_copy(const Group<G> &g, uint8_t *dst, u
 // shuffle scan, then every lane writes ITS token (literal header + payload + copy tag) on its own.
 // That replaces ~30 warp instructions per match in the serial chain by ~6 amortised ones.  Tokens
 // with a literal over 32 bytes or a copy over 64 bytes are written by the whole group instead.
-template <int G>
-__device__ __forceinline__ uint32_t flush_tokens(const Group<G> &g, uint8_t *dst, uint32_t op, uint32_t sin_a,
+template <int G, bool ST>
+__device__ __forceinline__ uint32_t flush_tokens(const Group<G> &g, uint8_t *dst, uint32_t op, const Input<ST> &in,
 						 uint32_t tok_a, uint32_t count)
 {
 	g.sync();
@@ -176,9 +224,8 @@ __device__ __forceinline__ uint32_t flush_tokens(const Group<G> &g, uint8_t *dst
 			uint8_t *d = dst + at;
 			if (litlen) {
 				*d++ = (uint8_t)((litlen - 1) << 2);
-				const uint32_t from = sin_a + ne;
 				for (uint32_t i = 0; i < litlen; ++i)
-					d[i] = (uint8_t)lds_u8(from + i);
+					d[i] = (uint8_t)in.u8(ne + i);
 				d += litlen;
 			}
 			uint32_t nb;
@@ -196,7 +243,7 @@ __device__ __forceinline__ uint32_t flush_tokens(const Group<G> &g, uint8_t *dst
 			const uint32_t bm = g.bcast(m, kk);
 			uint32_t o2 = g.bcast(at, kk);
 			if (blit)
-				o2 += emit_literal<G>(g, dst + o2, sin_a, bne, blit);
+				o2 += emit_literal<G, ST>(g, dst + o2, in, bne, blit);
 			emit_copy<G>(g, dst + o2, boff, bm);
 		}
 		op += g.bcast(incl, G - 1);
@@ -206,17 +253,18 @@ __device__ __forceinline__ uint32_t flush_tokens(const Group<G> &g, uint8_t *dst
 }
 
 // match extension, bounded by n (csnappy_compress.c:252-295): the first G bytes one byte per lane (most
-// copies end there), then 4*G bytes per step.  ip_a / cd_a: shared addresses of the two 4-byte-equal positions.
-template <int G>
-__device__ __forceinline__ uint32_t extend_match(const Group<G> &g, uint32_t ip_a, uint32_t cd_a, uint32_t room)
+// copies end there), then 4*G bytes per step.  ip / cd: the two 4-byte-equal positions, room = n - ip.
+template <int G, bool ST>
+__device__ __forceinline__ uint32_t extend_match(const Group<G> &g, const Input<ST> &in, uint32_t ip, uint32_t cd,
+						 uint32_t room)
 {
-	const unsigned ne = g.ballot(lds_u8(cd_a + 4 + g.lane) != lds_u8(ip_a + 4 + g.lane) || 4 + g.lane >= room);
+	const unsigned ne = g.ballot(in.u8(cd + 4 + g.lane) != in.u8(ip + 4 + g.lane) || 4 + g.lane >= room);
 	if (ne)
 		return 3 + __ffs(ne);
 	uint32_t m = 4 + G;
 	for (;;) {
 		const uint32_t d = min(m + 4 * g.lane, room);
-		const uint32_t x = lds32u_a(cd_a + d) ^ lds32u_a(ip_a + d);
+		const uint32_t x = in.u32(cd + d) ^ in.u32(ip + d);
 		uint32_t mk = x ? d + ((uint32_t)(__ffs(x) - 1) >> 3) : 0x7fffffffu;
 		mk = g.min(min(mk, room));
 		if (mk < m + 4 * G)
@@ -229,7 +277,7 @@ __device__ __forceinline__ uint32_t extend_match(const Group<G> &g, uint32_t ip_
 
 enum : int { ST_NEED = 0, ST_LOADING = 1, ST_RUN = 2 };
 
-template <int G>
+template <int G, bool ST>
 __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const CompressParams p)
 {
 	extern __shared__ __align__(128) uint8_t smem[];
@@ -242,7 +290,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 	uint16_t *tab = reinterpret_cast<uint16_t *>(gs);
 	uint8_t *sarea = gs + p.table_bytes;  // staged input, 16-byte aligned
 	const uint32_t sarea_a = smem_u32(sarea), tab_a = smem_u32(tab);
-	uint32_t sin_a = sarea_a;  // + (src & 15): shared address where the block's first byte lands
+	Input<ST> in;  // staged: sarea_a + (src & 15), the shared address where the block's first byte lands
 	const uint32_t bar = smem_u32(sarea + p.in_area), tok_a = bar + 16;
 	const unsigned full = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
 
@@ -305,9 +353,14 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 				for (uint32_t i = g.lane; i < nv; i += G)
 					t4[i] = z;
 			}
-			bool bulk;
-			sin_a = sarea_a + stage_block<G>(g, sarea, src, n, bar, &bulk);
-			state = bulk ? ST_LOADING : ST_RUN;
+			if constexpr (ST) {
+				bool bulk;
+				in.a = sarea_a + stage_block<G>(g, sarea, src, n, bar, &bulk);
+				state = bulk ? ST_LOADING : ST_RUN;
+			} else {
+				in.set(src, n);
+				state = ST_RUN;
+			}
 			g.sync();
 		}
 		if (state == ST_LOADING) {
@@ -337,7 +390,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 			const uint32_t pp = wbase + g.lane;
 			bool valid = pp < ip_limit && g.lane < cut;
 			// invalid lanes read on inside the staging pad (pp + 3 <= n + 19) and never store
-			const uint32_t bytes = lds32u_a(sin_a + pp);
+			const uint32_t bytes = in.u32(pp);
 			const uint32_t slot = tab_a + 2 * ((bytes * kHashMul) >> shift);
 			const uint32_t old = lds_u16(slot);
 			g.sync();
@@ -346,7 +399,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 			g.sync();
 			const uint32_t rb1 = lds_u16(slot);
 			const uint32_t cand = valid ? old : 0u;  // (blocks under 15 bytes never clear the table)
-			const uint32_t cb = lds32u_a(sin_a + cand);
+			const uint32_t cb = in.u32(cand);
 			const bool lost = valid && rb1 != pp;
 			done_fast = true;
 			if (g.ballot(lost)) {
@@ -395,10 +448,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 					}
 					const uint32_t f = __ffs(elig) - 1;
 					const uint32_t ip = wbase + f, cd = g.bcast(cand, (int)f);
-					const uint32_t m = extend_match<G>(g, sin_a + ip, sin_a + cd, n - ip);
+					const uint32_t m = extend_match<G, ST>(g, in, ip, cd, n - ip);
 					sts_v2(tok_a + 8 * ntok, next_emit | (ip << 16), cd | (m << 16));
 					if (++ntok == kTokens) {
-						op = flush_tokens<G>(g, dst, op, sin_a, tok_a, ntok);
+						op = flush_tokens<G, ST>(g, dst, op, in, tok_a, ntok);
 						ntok = 0;
 					}
 					next_emit = ip + m;
@@ -446,7 +499,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 			s = (32u + j0 + g.lane) >> 5;
 		}
 		const bool valid = pp + s <= ip_limit;
-		const uint32_t bytes = lds32u_a(sin_a + (valid ? pp : 0u));
+		const uint32_t bytes = in.u32(valid ? pp : 0u);
 		const uint32_t slot = tab_a + 2 * ((bytes * kHashMul) >> shift);
 		const uint32_t old = lds_u16(slot);
 		g.sync();
@@ -491,7 +544,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 				cand = lp;
 			g.sync();
 		}
-		const uint32_t cb = lds32u_a(sin_a + cand);
+		const uint32_t cb = in.u32(cand);
 		const unsigned H = g.ballot(valid && cb == bytes);
 		const unsigned V = g.ballot(valid);
 		const bool multi = uni && !exact;
@@ -518,11 +571,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 			}
 			const unsigned f = __ffs(elig) - 1;
 			const uint32_t ip = g.bcast(pp, (int)f), cd = g.bcast(cand, (int)f);
-			const uint32_t m = extend_match<G>(g, sin_a + ip, sin_a + cd, n - ip);
+			const uint32_t m = extend_match<G, ST>(g, in, ip, cd, n - ip);
 			// record the match; emission is deferred (flush_tokens)
 			sts_v2(tok_a + 8 * ntok, next_emit | (ip << 16), cd | (m << 16));
 			if (++ntok == kTokens) {
-				op = flush_tokens<G>(g, dst, op, sin_a, tok_a, ntok);
+				op = flush_tokens<G, ST>(g, dst, op, in, tok_a, ntok);
 				ntok = 0;
 			}
 			next_emit = ip + m;
@@ -564,10 +617,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 		} while (G == 32 && !fin);  // one group per warp: stay in the window loop until the block is parsed
 		if (fin) {
 			if (ntok)
-				op = flush_tokens<G>(g, dst, op, sin_a, tok_a, ntok);
+				op = flush_tokens<G, ST>(g, dst, op, in, tok_a, ntok);
 			ntok = 0;
 			if (next_emit < n)
-				op += emit_literal<G>(g, dst + op, sin_a, next_emit, n - next_emit);
+				op += emit_literal<G, ST>(g, dst + op, in, next_emit, n - next_emit);
 			if (g.lane == 0)
 				a.out_len[blk] = op;
 			state = ST_NEED;
@@ -579,13 +632,19 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 
 using namespace csb;
 
-template <int G>
+template <int G, bool ST>
 static int launch_compress_g(const CompressParams &p, int threads, int ctas, size_t smem, cudaStream_t s)
 {
-	cudaError_t e = cudaFuncSetAttribute(compress_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	cudaError_t e = cudaFuncSetAttribute(compress_kernel<G, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess)
 		return (int)e;
-	compress_kernel<G><<<ctas, threads, smem, s>>>(p);
+	if (!ST) {  // the input is read through L1: leave it whatever the tables do not need
+		e = cudaFuncSetAttribute(compress_kernel<G, ST>, cudaFuncAttributePreferredSharedMemoryCarveout,
+					 (int)((smem + 2048) * 100 / (228 * 1024) + 1));
+		if (e != cudaSuccess)
+			return (int)e;
+	}
+	compress_kernel<G, ST><<<ctas, threads, smem, s>>>(p);
 	count_launch();
 	return (int)cudaGetLastError();
 }
@@ -619,8 +678,32 @@ extern "C" int csb_launch_compress(const struct csb_compress_args *a, csb_stream
 		budget = di.smem_per_block_optin;
 	int groups = (int)(budget / p.group_smem);
 	const int max_groups = kMaxThreads / G;
+	// Blocks of which fewer than 8 fit an SM staged (fragments above ~14 KB with their table) are read from global
+	// memory instead: only the table stays in shared memory and about twice as many chains run per SM
+	// (32 KiB / wm 15: 7 instead of 3).  stage_input: 0 = this rule, 1 = always stage, 2 = never stage.
+	bool staged = true;
+	if (G == 32 && a->stage_input != 1) {
+		const uint32_t lean = p.table_bytes + 16 + 8 * kTokens;
+		const int lean_groups = (int)(budget / lean) < max_groups ? (int)(budget / lean) : max_groups;
+		// (a batch that fits the staged slots of the machine in one go gains nothing from more slots)
+		if (a->stage_input == 2 || (groups < 8 && lean_groups > groups && a->n_blocks > (uint32_t)(di.sm_count * (groups > 0 ? groups : 1)))) {
+			staged = false;
+			p.in_area = 0;
+			p.group_smem = lean;
+			groups = lean_groups;
+		}
+	}
 	if (groups > max_groups)
 		groups = max_groups;
+	{
+		static int cap_env = -1;  // experiments: CSB_COMPRESS_GROUPS caps the groups per CTA (the rest of the array stays L1)
+		if (cap_env < 0) {
+			const char *e = getenv("CSB_COMPRESS_GROUPS");
+			cap_env = e ? atoi(e) : 0;
+		}
+		if (cap_env > 0 && groups > cap_env)
+			groups = cap_env;
+	}
 	if (groups < 1)
 		return (int)cudaErrorInvalidConfiguration;
 	long want = ((long)a->n_blocks + groups - 1) / groups;
@@ -645,9 +728,12 @@ extern "C" int csb_launch_compress(const struct csb_compress_args *a, csb_stream
 		return (int)ce;
 	p.counter = counter;
 	switch (G) {
-	case 32: e = launch_compress_g<32>(p, threads, (int)ctas, smem, s); break;
-	case 16: e = launch_compress_g<16>(p, threads, (int)ctas, smem, s); break;
-	case 8: e = launch_compress_g<8>(p, threads, (int)ctas, smem, s); break;
+	case 32:
+		e = staged ? launch_compress_g<32, true>(p, threads, (int)ctas, smem, s)
+			   : launch_compress_g<32, false>(p, threads, (int)ctas, smem, s);
+		break;
+	case 16: e = launch_compress_g<16, true>(p, threads, (int)ctas, smem, s); break;
+	case 8: e = launch_compress_g<8, true>(p, threads, (int)ctas, smem, s); break;
 	default: e = (int)cudaErrorInvalidValue; break;
 	}
 	return e;

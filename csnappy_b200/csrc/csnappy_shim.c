@@ -65,7 +65,7 @@ int csnappy_b200_device_ok(void) { return csnappy_b200_device_count() > 0; }
 uint64_t csnappy_b200_kernel_launches(void) { return csb_launch_count(); }
 
 /* ---- tuning knobs ------------------------------------------------------- */
-static int g_compress_lanes, g_decompress_lanes, g_ctas_per_sm, g_stage_input, g_smem_kb, g_host_register, g_stream_min, g_lane_warps, g_copy_threads, g_no_bounce;
+static int g_compress_lanes, g_decompress_lanes, g_ctas_per_sm, g_stage_input, g_smem_kb, g_host_register, g_stream_min, g_lane_warps, g_copy_threads, g_no_bounce, g_compress_stage;
 
 int csnappy_b200_set_tuning(const char *key, int value)
 {
@@ -78,6 +78,12 @@ int csnappy_b200_set_tuning(const char *key, int value)
 			g_compress_lanes = value;
 		else
 			g_decompress_lanes = value;
+		return 0;
+	}
+	if (!strcmp(key, "compress_stage_input")) { /* 0: choose; 1: always stage blocks in shared memory; 2: never */
+		if (value < 0 || value > 2)
+			return CSNAPPY_E_BAD_ARG;
+		g_compress_stage = value;
 		return 0;
 	}
 	if (!strcmp(key, "decompress_stage_input")) {
@@ -165,6 +171,7 @@ static void fill_compress_args(struct csb_compress_args *a)
 	memset(a, 0, sizeof(*a));
 	a->lanes = g_compress_lanes;
 	a->ctas_per_sm = g_ctas_per_sm;
+	a->stage_input = g_compress_stage;
 }
 
 static void fill_decompress_args(struct csb_decompress_args *a)

@@ -34,6 +34,7 @@ struct csb_compress_args {
 	int lanes;		/* lanes cooperating on one block: 8, 16, 32 (0 = default) */
 	int ctas_per_sm;	/* 0 = default */
 	uint32_t *counter;	/* device word for the block claim counter (NULL: a word of the per-device ring, pack_kernel.cu next_counter) */
+	int stage_input;	/* 0: choose; 1: always stage the block in shared memory; 2: read it from global memory (32-lane groups) */
 };
 
 struct csb_decompress_args {

@@ -129,20 +129,24 @@ def _to_dev(pages, stride):
 
 
 def _gpu_compress(cs, pages, block, wm, lanes=0, var_len=False):
-    cs.set_tuning("compress_lanes", lanes)
+    """lanes: 0 / 8 / 16 / 32 = lane group (block staged in shared memory as the launcher decides);
+    -32 = 32-lane groups reading the block from global memory (the form large fragments take in large batches)"""
+    cs.set_tuning("compress_stage_input", 2 if lanes < 0 else 0)
+    cs.set_tuning("compress_lanes", abs(lanes))
     try:
         d_in, d_len, _, _ = _to_dev(pages, block)
         out, out_len = cs.batch_compress_fragments(d_in, block, len(pages), wm, in_len=d_len if var_len else None)
         torch.cuda.synchronize()
     finally:
         cs.set_tuning("compress_lanes", 0)
+        cs.set_tuning("compress_stage_input", 0)
     ostride = cs.api.out_stride_for(block)
     o = out.cpu().numpy().reshape(-1)[: len(pages) * ostride].reshape(len(pages), ostride)
     ln = out_len.cpu().numpy().astype(np.uint32)
     return [o[i, : ln[i]].tobytes() for i in range(len(pages))], out, out_len
 
 
-@pytest.mark.parametrize("lanes", [32, 16, 8])
+@pytest.mark.parametrize("lanes", [32, 16, 8, -32])
 @pytest.mark.parametrize("key", ["4096/13", "32768/15", "32768/16", "4096/9", "4096/16"])
 def test_batch_compress_urls_fragments(cs, golden, urls, key, lanes):
     block, wm = map(int, key.split("/"))
@@ -153,7 +157,7 @@ def test_batch_compress_urls_fragments(cs, golden, urls, key, lanes):
     assert (len(comp), sum(map(len, comp)), sha(stream)) == (g["blocks"], g["total"], g["sha256"])
 
 
-@pytest.mark.parametrize("lanes", [32, 16, 8])
+@pytest.mark.parametrize("lanes", [32, 16, 8, -32])
 @pytest.mark.parametrize("size,wm", [(4096, 13), (4096, 9), (32768, 15), (32768, 16), (1000, 12), (20000, 14), (64, 10)])
 def test_batch_compress_fuzz_vs_oracle(cs, chk, size, wm, lanes):
     pages = fuzz_pages(4321 + size + wm, 70, size)
@@ -167,10 +171,10 @@ def test_batch_compress_edge_sizes(cs, chk):
     text = bytes(rng.integers(97, 101, 40000, dtype=np.uint8))
     sizes = list(range(0, 40)) + [59, 60, 61, 62, 255, 256, 257, 258] + list(range(4081, 4112)) + list(range(32753, 32769))
     pages = [text[:n] for n in sizes]
-    for wm in (9, 13, 16):
-        comp, _, _ = _gpu_compress(cs, pages, 32768, wm, var_len=True)
+    for wm, lanes in ((9, 0), (13, 0), (16, 0), (13, -32), (15, -32)):
+        comp, _, _ = _gpu_compress(cs, pages, 32768, wm, lanes, var_len=True)
         for n, c in zip(sizes, comp):
-            assert c == chk.compress_fragment(text[:n], wm), (n, wm)
+            assert c == chk.compress_fragment(text[:n], wm), (n, wm, lanes)
 
 
 def test_batch_compress_shrink_table_flag(cs, chk):

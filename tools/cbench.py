@@ -13,6 +13,8 @@ only = sys.argv[1] if len(sys.argv) > 1 else "text"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 262144
 L = int(sys.argv[3]) if len(sys.argv) > 3 else 4096
 wm = int(sys.argv[4]) if len(sys.argv) > 4 else 13
+stage = int(sys.argv[5]) if len(sys.argv) > 5 else 0  # compress_stage_input: 0 auto, 1 staged, 2 read from global
+cs.set_tuning("compress_stage_input", stage)
 if L > 4096:
     d = synth.text_fragments(n, L, device="cuda")
 else:
@@ -31,4 +33,4 @@ for _ in range(5):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 5
-print(f"{only} unit {L} wm {wm} n {n}: compress {n * L / ms / 1e6:.1f} GB/s  ({ms:.3f} ms)  ratio {float(olen.sum()) / (n * L):.4f}", flush=True)
+print(f"{only} unit {L} wm {wm} n {n} stage {stage}: compress {n * L / ms / 1e6:.1f} GB/s  ({ms:.3f} ms)  ratio {float(olen.sum()) / (n * L):.4f}", flush=True)

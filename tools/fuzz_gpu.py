@@ -34,6 +34,8 @@ while time.time() - t0 < budget:
         host[i] = np.frombuffer(p, dtype=np.uint8)
     cs.set_tuning("compress_lanes", lanes)
     cs.set_tuning("decompress_lanes", lanes)
+    cs.set_tuning("compress_stage_input", int(rng.choice([0, 1, 2])) if lanes == 32 else 0)  # staged / read from global
+    cs.set_tuning("decompress_stage_input", int(rng.choice([0, 0, 1, 3, 4])))  # default routing / staged / global / lane
     d_in, d_len = torch.from_numpy(host).cuda(), torch.from_numpy(lens).cuda()
     out, out_len = cs.batch_compress_fragments(d_in, size, count, wm, in_len=d_len)
     torch.cuda.synchronize()
@@ -81,5 +83,7 @@ while time.time() - t0 < budget:
     rounds += 1
 cs.set_tuning("compress_lanes", 0)
 cs.set_tuning("decompress_lanes", 0)
+cs.set_tuning("compress_stage_input", 0)
+cs.set_tuning("decompress_stage_input", 0)
 print(f"fuzz ok: {rounds} rounds, {blocks} blocks compressed byte-identically, {streams} streams decoded with identical results "
       f"in {time.time() - t0:.0f} s")
