@@ -188,14 +188,22 @@ int csnappy_b200_device_ok(void);	   /* 1 if a CUDA device is usable */
 int csnappy_b200_device_count(void);	   /* visible CUDA devices (0 on error) */
 const char *csnappy_b200_last_error(void); /* text of the last device error (thread local) */
 uint64_t csnappy_b200_kernel_launches(void); /* kernels launched by this library so far */
-/* key: "compress_lanes" | "decompress_lanes" (lanes cooperating on one block: 8/16/32),
- *      "ctas_per_sm", "decompress_stage_input" (1: always stage blocks in shared memory, 2: stage only
- *      the output and read compressed blocks through L1, 3: never stage -- decode against global memory), "decompress_smem_kb" (shared memory per SM in unstaged mode);
- *      4: one lane per block (the default for very large batches);
- *      "host_register" (1: page-lock the caller's buffers for the duration of a host-buffer call: worth it for big
- *      pageable buffers that are reused), "stream_decode_min" (bytes from which one single stream takes the parallel
- *      stream decoder; -1: never);
- *      value 0 restores the default.  Returns 0 or CSNAPPY_E_BAD_ARG. */
+/* key (value 0 restores the default; returns 0 or CSNAPPY_E_BAD_ARG):
+ *   "compress_lanes" | "decompress_lanes"  lanes cooperating on one block in the warp-per-block kernels: 8 / 16 / 32
+ *   "compress_stage_input"    1: always stage blocks in shared memory; 2: read them from global memory (32-lane
+ *                             groups only; the default for large batches of fragments above ~14 KB)
+ *   "decompress_stage_input"  1: always stage blocks in shared memory; 2: stage only the output and read the
+ *                             compressed block through L1; 3: decode against global memory, a warp per block;
+ *                             4: one lane per block (the default for very large batches)
+ *   "decompress_lane_warps"   lane-per-block decoder: warps of 32 blocks in flight per SM (default 32)
+ *   "decompress_smem_kb"      shared memory per SM in mode 2
+ *   "ctas_per_sm"             resident CTAs per SM of the warp-per-block kernels
+ *   "stream_decode_min"       bytes from which ONE single stream takes the parallel stream decoder; -1: never
+ *   "copy_threads"            helper threads that stage PAGEABLE caller memory through pinned buffers in the
+ *                             host-buffer pipelines (read when the pool starts; default 7 on >= 16 cores)
+ *   "no_bounce"               1: hand pageable caller memory straight to cudaMemcpyAsync (round-1 behaviour)
+ *   "host_register"           1: page-lock the caller's buffers for the duration of a host-buffer call (measured
+ *                             slower than the staging above unless the same buffers are registered once by the caller) */
 int csnappy_b200_set_tuning(const char *key, int value);
 
 #ifdef __cplusplus
