@@ -4,28 +4,32 @@
 // (/root/reference/csnappy_compress.c:469-606) for the same input and table size.
 //
 // The reference's greedy parse is a serial dependency chain (every probe reads and
-// overwrites a hash slot), so the kernel is bound by instruction issue and shared-memory
-// latency, not by HBM (profiles/).  The design therefore minimises warp instructions per
-// block and keeps every resident block busy:
+// overwrites a hash slot), so the kernel is bound by the latency of one dependent chain per
+// block times the blocks that fit on chip, not by HBM (profiles/).  The design
+// therefore minimises the dependent instructions per block and keeps every resident block busy:
 //
 //   * one GROUP of G lanes (8, 16 or 32: a slice of one warp) per block; a persistent CTA per
 //     SM holds as many groups as shared memory allows (u16 hash table of 1<<wm bytes + the
 //     staged input: 18 x 4 KiB pages per SM at wm 13); groups claim blocks from a global counter;
 //   * the block is staged with ONE bulk async copy (cp.async.bulk -> UBLKCP, completion on an
 //     mbarrier) issued by one lane while the group clears its hash table;
-//   * the whole parse is ONE uniform loop of "probe steps".  A probe step evaluates G
-//     consecutive probe positions of the reference's scan at once -- they depend only on the
-//     skip counter (csnappy_compress.c:535-542) -- resolves equal-hash lanes with match.any,
-//     finds the first hit with ballot/ffs and commits exactly the table writes the serial code
-//     would have made.  The post-copy bookkeeping of the reference (insert ip-1, re-probe ip,
-//     csnappy_compress.c:587-593) is folded into the same step: lane 0 inserts ip-1, lane 1
-//     probes ip, lanes 2.. already run the next scan from ip+1, because that is exactly the
-//     order in which the serial code touches the table;
-//   * match extension compares 4*G bytes per step and reduces with redux.min; literals and
-//     copy tags are written straight to the block's HBM slot with lane-parallel byte stores
-//     (L2 merges them; the kernel is nowhere near the HBM roofline);
-//   * the per-group control flow is a flat state machine (claim / wait for the bulk copy /
-//     step), so the groups sharing a warp never wait for each other at block boundaries.
+//   * the parse is a loop of "probe steps".  A probe step evaluates G consecutive probe positions of the
+//     reference's scan at once -- they depend only on the skip counter (csnappy_compress.c:535-542) -- finds the
+//     first hit with ballot/ffs and commits exactly the table writes the serial code would have made.  The
+//     post-copy bookkeeping of the reference (insert ip-1, re-probe ip, csnappy_compress.c:587-593) is folded
+//     into the same step: lane 0 inserts ip-1, lane 1 probes ip, lanes 2.. already run the next scan from ip+1,
+//     because that is exactly the order in which the serial code touches the table.  Two forms of the step:
+//     a FAST PATH for 32 consecutive positions without shared hash slots (slot pairs are told apart by a second
+//     insert + readback and the window is cut in front of the first conflicting lane; the parse continues
+//     inside the window after a copy), and a GENERAL path (strided windows, three lanes on one slot -> match.any,
+//     16- and 8-lane groups);
+//   * match extension compares 4*G bytes per step and reduces with redux.min; emission is DEFERRED: the chain
+//     stores an 8-byte token per match and every 32 tokens the group writes them out together, each lane its own
+//     literal + copy tag, with byte stores straight into the block's HBM slot (L2 merges them);
+//   * the per-group control flow is a flat state machine (claim / wait for the bulk copy / step), so the groups
+//     sharing a warp never wait for each other at block boundaries; 32-lane groups stay in an inner window loop;
+//   * fragments too large to stage in useful numbers (32 KiB + a 32 KiB table: 3 per SM) are read from global
+//     memory instead (Input<false>): only the table stays in shared memory, 7 chains per SM.
 #include <stdlib.h>
 
 #include "device_common.cuh"
@@ -258,9 +262,15 @@ template <int G, bool ST>
 __device__ __forceinline__ uint32_t extend_match(const Group<G> &g, const Input<ST> &in, uint32_t ip, uint32_t cd,
 						 uint32_t room)
 {
+#ifndef CSB_EXT_BALLOT  // redux.min on the first mismatching lane: measured +1.7 % over ballot + ffs
+	const uint32_t first = g.min((in.u8(cd + 4 + g.lane) != in.u8(ip + 4 + g.lane) || 4 + g.lane >= room) ? g.lane : (uint32_t)G);
+	if (first < (uint32_t)G)
+		return 4 + first;
+#else
 	const unsigned ne = g.ballot(in.u8(cd + 4 + g.lane) != in.u8(ip + 4 + g.lane) || 4 + g.lane >= room);
 	if (ne)
 		return 3 + __ffs(ne);
+#endif
 	uint32_t m = 4 + G;
 	for (;;) {
 		const uint32_t d = min(m + 4 * g.lane, room);
@@ -372,83 +382,207 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 
 		bool fin;
 		do {
-		fin = false;
-		// ---- fast path (G == 32): a window of CONSECUTIVE positions in which no two lanes share a hash slot ----
-		// The common window of compressible data: lanes 0..cut-1 probe wbase + lane with stride 1 (probe indices
-		// j0 + lane <= 31: page start, right behind a copy, or the stride-1 head of a later window), so
-		// ip = wbase + lane needs no shuffle, "all lanes valid" is a scalar test, and with every slot private to one
-		// lane the table entries read before the inserts ARE the candidates the serial code sees, however many
-		// copies the window holds.  The candidate bytes are loaded before the readback is evaluated (both depend
-		// only on `old`).  Two lanes on one slot (a third of the windows on URL text: repeated 4-byte groups) are
-		// told apart by a second insert + readback -- after it each lane of a pair knows its partner's position --
-		// and the window is CUT in front of the first lane that has a lower partner: the lanes before it are
-		// conflict-free, the lanes from it on take their inserts back and are probed again by the next window.
-		// Three or more lanes on one slot restore the table and hand the window to the general code below.
-		bool done_fast = false;
-		if (G == 32 && j0 < 24) {
-			uint32_t cut = j0 > 0 ? 32u - (uint32_t)j0 : 32u;
-			const uint32_t pp = wbase + g.lane;
-			bool valid = pp < ip_limit && g.lane < cut;
-			// invalid lanes read on inside the staging pad (pp + 3 <= n + 19) and never store
-			const uint32_t bytes = in.u32(pp);
-			const uint32_t slot = tab_a + 2 * ((bytes * kHashMul) >> shift);
-			const uint32_t old = lds_u16(slot);
-			g.sync();
-			if (valid)
-				sts_u16(slot, pp);
-			g.sync();
-			const uint32_t rb1 = lds_u16(slot);
-			const uint32_t cand = valid ? old : 0u;  // (blocks under 15 bytes never clear the table)
-			const uint32_t cb = in.u32(cand);
-			const bool lost = valid && rb1 != pp;
-			done_fast = true;
-			if (g.ballot(lost)) {
+			fin = false;
+			// ---- fast path (G == 32): a window of CONSECUTIVE positions in which no two lanes share a hash slot ----
+			// The common window of compressible data: lanes 0..cut-1 probe wbase + lane with stride 1 (probe indices
+			// j0 + lane <= 31: page start, right behind a copy, or the stride-1 head of a later window), so
+			// ip = wbase + lane needs no shuffle, "all lanes valid" is a scalar test, and with every slot private to one
+			// lane the table entries read before the inserts ARE the candidates the serial code sees, however many
+			// copies the window holds.  The candidate bytes are loaded before the readback is evaluated (both depend
+			// only on `old`).  Two lanes on one slot (a third of the windows on URL text: repeated 4-byte groups) are
+			// told apart by a second insert + readback -- after it each lane of a pair knows its partner's position --
+			// and the window is CUT in front of the first lane that has a lower partner: the lanes before it are
+			// conflict-free, the lanes from it on take their inserts back and are probed again by the next window.
+			// Three or more lanes on one slot restore the table and hand the window to the general code below.
+			bool done_fast = false;
+			if (G == 32 && j0 < 24) {
+				uint32_t cut = j0 > 0 ? 32u - (uint32_t)j0 : 32u;
+				const uint32_t pp = wbase + g.lane;
+				bool valid = pp < ip_limit && g.lane < cut;
+				// invalid lanes read on inside the staging pad (pp + 3 <= n + 19) and never store
+				const uint32_t bytes = in.u32(pp);
+				const uint32_t slot = tab_a + 2 * ((bytes * kHashMul) >> shift);
+				const uint32_t old = lds_u16(slot);
 				g.sync();
-				if (lost)
+				if (valid)
 					sts_u16(slot, pp);
 				g.sync();
-				const uint32_t rb2 = lds_u16(slot);
-				const bool triple = g.ballot(lost && rb2 != pp) != 0;
-				g.sync();  // every lane has read back before anybody rewrites
-				if (triple) {
-					if (valid)
-						sts_u16(slot, old);
-					done_fast = false;
-				} else {
-					const uint32_t q = lost ? rb1 : rb2;  // the partner's position (own position: none)
-					const bool hasp = valid && q != pp;
-					const uint32_t pl = q - wbase;
-					cut = __ffs(g.ballot(hasp && q < pp)) - 1;  // first lane with a lower partner (there is one)
-					const bool upper = g.lane >= cut;
-					// lanes from the cut on leave the table as if they had never inserted; a lane in front of the
-					// cut whose partner is behind it owns the slot again
-					const bool wr_old = valid && upper && (!hasp || (pl >= cut && g.lane < pl));
-					const bool wr_pp = valid && !upper && hasp;
-					if (wr_old || wr_pp)
-						sts_u16(slot, wr_pp ? pp : old);
-					valid = valid && !upper;
+				const uint32_t rb1 = lds_u16(slot);
+				const uint32_t cand = valid ? old : 0u;  // (blocks under 15 bytes never clear the table)
+				const uint32_t cb = in.u32(cand);
+				const bool lost = valid && rb1 != pp;
+				done_fast = true;
+				if (g.ballot(lost)) {
+					g.sync();
+					if (lost)
+						sts_u16(slot, pp);
+					g.sync();
+					const uint32_t rb2 = lds_u16(slot);
+					const bool triple = g.ballot(lost && rb2 != pp) != 0;
+					g.sync();  // every lane has read back before anybody rewrites
+					if (triple) {
+						if (valid)
+							sts_u16(slot, old);
+						done_fast = false;
+					} else {
+						const uint32_t q = lost ? rb1 : rb2;  // the partner's position (own position: none)
+						const bool hasp = valid && q != pp;
+						const uint32_t pl = q - wbase;
+						cut = __ffs(g.ballot(hasp && q < pp)) - 1;  // first lane with a lower partner (there is one)
+						const bool upper = g.lane >= cut;
+						// lanes from the cut on leave the table as if they had never inserted; a lane in front of the
+						// cut whose partner is behind it owns the slot again
+						const bool wr_old = valid && upper && (!hasp || (pl >= cut && g.lane < pl));
+						const bool wr_pp = valid && !upper && hasp;
+						if (wr_old || wr_pp)
+							sts_u16(slot, wr_pp ? pp : old);
+						valid = valid && !upper;
+					}
+					g.sync();
 				}
-				g.sync();
+				if (done_fast) {
+					const unsigned H = g.ballot(valid && cb == bytes);
+					const bool all_valid = wbase + cut - 1 < ip_limit;
+					uint32_t cur = t;
+					for (;;) {
+						const unsigned elig = H & (0xffffffffu << cur);
+						if (!elig) {
+							if (!all_valid) {
+								fin = true;  // ran into ip_limit without a hit
+							} else {
+								wbase += cut;
+								j0 += (int)cut;
+								t = 0;
+							}
+							break;
+						}
+						const uint32_t f = __ffs(elig) - 1;
+						const uint32_t ip = wbase + f, cd = g.bcast(cand, (int)f);
+						const uint32_t m = extend_match<G, ST>(g, in, ip, cd, n - ip);
+						sts_v2(tok_a + 8 * ntok, next_emit | (ip << 16), cd | (m << 16));
+						if (++ntok == kTokens) {
+							op = flush_tokens<G, ST>(g, dst, op, in, tok_a, ntok);
+							ntok = 0;
+						}
+						next_emit = ip + m;
+						if (next_emit >= ip_limit) {
+							fin = true;
+							break;
+						}
+						const uint32_t nl = next_emit - wbase;  // lane of the re-probe position
+						// lanes skipped by the copy never insert: undo (ip-1 = lane nl-1 stays, ip = lane nl goes on)
+						if (valid && g.lane > f && g.lane + 1 < nl)
+							sts_u16(slot, old);
+						if (nl >= cut) {
+							wbase = next_emit - 1;
+							j0 = -2;
+							t = 1;
+							break;
+						}
+						cur = nl;
+						j0 = -(int)(nl + 1);
+					}
+					if (!fin)
+						g.sync();
+				}
 			}
-			if (done_fast) {
+			if (!done_fast) {
+				// ---- one WINDOW of G probe positions (csnappy_compress.c:535-552 and 587-593) ----
+				// Lane k probes the k-th position of the window.  j0 + k is that probe's index in the
+				// reference's skip schedule (stride (32 + index) >> 5); lanes whose index is negative
+				// are the post-copy bookkeeping positions (t == 1: lane 0 = ip-1, insert only; lane 1 =
+				// ip, the re-probe) or lie before an in-window scan restart.  While every stride in the
+				// window is 1 ("uni") the window is G consecutive bytes and the parse can CONTINUE
+				// inside it after a copy: the lanes behind the copy already hold their hash, table
+				// entry and compare result, and those stay valid as long as no two lanes of the window
+				// share a hash slot.  That is checked by inserting speculatively and reading back;
+				// lanes that turn out not to insert (skipped by a copy, or behind the end) undo.
+				const bool uni = j0 <= 32 - G;
+				uint32_t pp, s;
+				if (uni) {
+					pp = wbase + g.lane;
+					s = 1;
+				} else {
+					const uint32_t s0 = (32u + j0) >> 5;
+					const int jb = ((j0 >> 5) + 1) << 5;  // first probe index with stride s0 + 1
+					pp = wbase + g.lane * s0 + max(j0 + (int)g.lane - jb, 0);
+					s = (32u + j0 + g.lane) >> 5;
+				}
+				const bool valid = pp + s <= ip_limit;
+				const uint32_t bytes = in.u32(valid ? pp : 0u);
+				const uint32_t slot = tab_a + 2 * ((bytes * kHashMul) >> shift);
+				const uint32_t old = lds_u16(slot);
+				g.sync();
+				if (valid)
+					sts_u16(slot, pp);
+				g.sync();
+				const uint32_t rb1 = lds_u16(slot);
+				const bool lost = valid && rb1 != pp;
+				const bool exact = g.ballot(lost) != 0;	 // two lanes share a slot
+				// candidate: the table -- or, with shared slots, the latest lower lane with the same hash
+				// (invalid lanes must not follow a stale entry: blocks under 15 bytes never clear the table)
+				uint32_t cand = valid ? old : 0u;
+				unsigned same = 0;
+				if (exact) {
+					// Who shares a slot with whom?  For the common case of PAIRS in a window of consecutive
+					// positions a second insert + readback answers it (the loser of the first round saw the
+					// winner's position; after the losers insert, the winner sees its loser); three or more
+					// lanes on one slot, or a strided window, fall back to match.any (slow: ~300 cycles).
+					bool paired = false;
+					if (uni) {
+						g.sync();
+						if (lost)
+							sts_u16(slot, pp);
+						g.sync();
+						const uint32_t rb2 = lds_u16(slot);
+						if (!g.ballot(lost && rb2 != pp)) {
+							paired = true;
+							const uint32_t q = lost ? rb1 : rb2;  // the partner's position (own position: none)
+							same = 1u << g.lane;
+							if (valid && q != pp)
+								same |= 1u << (q - wbase);
+						}
+					}
+					g.sync();  // every lane has read back before anybody restores
+					if (valid)
+						sts_u16(slot, old);  // back to the state before this window
+					if (!paired)
+						same = g.match(valid ? slot : (0x80000000u | g.lane));
+					const unsigned lower = same & ((1u << g.lane) - 1u);
+					const uint32_t lp = g.bcast(pp, lower ? 31 - __clz(lower) : (int)g.lane);
+					if (lower)
+						cand = lp;
+					g.sync();
+				}
+				const uint32_t cb = in.u32(cand);
 				const unsigned H = g.ballot(valid && cb == bytes);
-				const bool all_valid = wbase + cut - 1 < ip_limit;
-				uint32_t cur = t;
+				const unsigned V = g.ballot(valid);
+				const bool multi = uni && !exact;
+
+				uint32_t cur = t;      // first lane that may hit
+				unsigned fhit = 32;    // exact windows: the (single) hit lane
 				for (;;) {
-					const unsigned elig = H & (0xffffffffu << cur);
+					const unsigned elig = H & (full << cur) & full;
 					if (!elig) {
-						if (!all_valid) {
+						if (V != full) {
 							fin = true;  // ran into ip_limit without a hit
+						} else if (uni) {
+							wbase += G;
+							j0 += G;
+							t = 0;
 						} else {
-							wbase += cut;
-							j0 += (int)cut;
+							const uint32_t s0 = (32u + j0) >> 5;
+							const int jb = ((j0 >> 5) + 1) << 5;
+							wbase += G * s0 + max(j0 + G - jb, 0);
+							j0 += G;
 							t = 0;
 						}
 						break;
 					}
-					const uint32_t f = __ffs(elig) - 1;
-					const uint32_t ip = wbase + f, cd = g.bcast(cand, (int)f);
+					const unsigned f = __ffs(elig) - 1;
+					const uint32_t ip = g.bcast(pp, (int)f), cd = g.bcast(cand, (int)f);
 					const uint32_t m = extend_match<G, ST>(g, in, ip, cd, n - ip);
+					// record the match; emission is deferred (flush_tokens)
 					sts_v2(tok_a + 8 * ntok, next_emit | (ip << 16), cd | (m << 16));
 					if (++ntok == kTokens) {
 						op = flush_tokens<G, ST>(g, dst, op, in, tok_a, ntok);
@@ -459,161 +593,37 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 						fin = true;
 						break;
 					}
-					const uint32_t nl = next_emit - wbase;  // lane of the re-probe position
-					// lanes skipped by the copy never insert: undo (ip-1 = lane nl-1 stays, ip = lane nl goes on)
-					if (valid && g.lane > f && g.lane + 1 < nl)
-						sts_u16(slot, old);
-					if (nl >= cut) {
+					// lane of the re-probe position if the parse can stay inside this window
+					const uint32_t nl = uni ? next_emit - wbase : 0x7fffffffu;
+					if (!exact) {
+						// lanes skipped by the copy never insert: undo (ip-1 = lane nl-1 stays, ip = lane nl goes on)
+						if (valid && g.lane > f && g.lane + 1 < nl)
+							sts_u16(slot, old);
+					} else {
+						fhit = f;
+					}
+					if (!multi || nl >= (uint32_t)G) {
 						wbase = next_emit - 1;
 						j0 = -2;
 						t = 1;
 						break;
 					}
+					// continue inside the window: lane nl-1 inserted ip-1, lane nl re-probes, scan restarts at nl+1
 					cur = nl;
 					j0 = -(int)(nl + 1);
 				}
-				if (!fin)
+				if (!fin) {
+					if (exact) {
+						// the table is in its pre-window state: lanes up to the hit insert, the highest lane
+						// of an equal-hash run owns the slot
+						const unsigned I = fhit < 32 ? ((2u << fhit) - 1u) : 0xffffffffu;
+						const unsigned rivals = same & I & ~((2u << g.lane) - 1u);
+						if (valid && ((I >> g.lane) & 1u) && !rivals)
+							sts_u16(slot, pp);
+					}
 					g.sync();
-			}
-		}
-		if (!done_fast) {
-		// ---- one WINDOW of G probe positions (csnappy_compress.c:535-552 and 587-593) ----
-		// Lane k probes the k-th position of the window.  j0 + k is that probe's index in the
-		// reference's skip schedule (stride (32 + index) >> 5); lanes whose index is negative
-		// are the post-copy bookkeeping positions (t == 1: lane 0 = ip-1, insert only; lane 1 =
-		// ip, the re-probe) or lie before an in-window scan restart.  While every stride in the
-		// window is 1 ("uni") the window is G consecutive bytes and the parse can CONTINUE
-		// inside it after a copy: the lanes behind the copy already hold their hash, table
-		// entry and compare result, and those stay valid as long as no two lanes of the window
-		// share a hash slot.  That is checked by inserting speculatively and reading back;
-		// lanes that turn out not to insert (skipped by a copy, or behind the end) undo.
-		const bool uni = j0 <= 32 - G;
-		uint32_t pp, s;
-		if (uni) {
-			pp = wbase + g.lane;
-			s = 1;
-		} else {
-			const uint32_t s0 = (32u + j0) >> 5;
-			const int jb = ((j0 >> 5) + 1) << 5;  // first probe index with stride s0 + 1
-			pp = wbase + g.lane * s0 + max(j0 + (int)g.lane - jb, 0);
-			s = (32u + j0 + g.lane) >> 5;
-		}
-		const bool valid = pp + s <= ip_limit;
-		const uint32_t bytes = in.u32(valid ? pp : 0u);
-		const uint32_t slot = tab_a + 2 * ((bytes * kHashMul) >> shift);
-		const uint32_t old = lds_u16(slot);
-		g.sync();
-		if (valid)
-			sts_u16(slot, pp);
-		g.sync();
-		const uint32_t rb1 = lds_u16(slot);
-		const bool lost = valid && rb1 != pp;
-		const bool exact = g.ballot(lost) != 0;	 // two lanes share a slot
-		// candidate: the table -- or, with shared slots, the latest lower lane with the same hash
-		// (invalid lanes must not follow a stale entry: blocks under 15 bytes never clear the table)
-		uint32_t cand = valid ? old : 0u;
-		unsigned same = 0;
-		if (exact) {
-			// Who shares a slot with whom?  For the common case of PAIRS in a window of consecutive
-			// positions a second insert + readback answers it (the loser of the first round saw the
-			// winner's position; after the losers insert, the winner sees its loser); three or more
-			// lanes on one slot, or a strided window, fall back to match.any (slow: ~300 cycles).
-			bool paired = false;
-			if (uni) {
-				g.sync();
-				if (lost)
-					sts_u16(slot, pp);
-				g.sync();
-				const uint32_t rb2 = lds_u16(slot);
-				if (!g.ballot(lost && rb2 != pp)) {
-					paired = true;
-					const uint32_t q = lost ? rb1 : rb2;  // the partner's position (own position: none)
-					same = 1u << g.lane;
-					if (valid && q != pp)
-						same |= 1u << (q - wbase);
 				}
-			}
-			g.sync();  // every lane has read back before anybody restores
-			if (valid)
-				sts_u16(slot, old);  // back to the state before this window
-			if (!paired)
-				same = g.match(valid ? slot : (0x80000000u | g.lane));
-			const unsigned lower = same & ((1u << g.lane) - 1u);
-			const uint32_t lp = g.bcast(pp, lower ? 31 - __clz(lower) : (int)g.lane);
-			if (lower)
-				cand = lp;
-			g.sync();
-		}
-		const uint32_t cb = in.u32(cand);
-		const unsigned H = g.ballot(valid && cb == bytes);
-		const unsigned V = g.ballot(valid);
-		const bool multi = uni && !exact;
-
-		uint32_t cur = t;      // first lane that may hit
-		unsigned fhit = 32;    // exact windows: the (single) hit lane
-		for (;;) {
-			const unsigned elig = H & (full << cur) & full;
-			if (!elig) {
-				if (V != full) {
-					fin = true;  // ran into ip_limit without a hit
-				} else if (uni) {
-					wbase += G;
-					j0 += G;
-					t = 0;
-				} else {
-					const uint32_t s0 = (32u + j0) >> 5;
-					const int jb = ((j0 >> 5) + 1) << 5;
-					wbase += G * s0 + max(j0 + G - jb, 0);
-					j0 += G;
-					t = 0;
-				}
-				break;
-			}
-			const unsigned f = __ffs(elig) - 1;
-			const uint32_t ip = g.bcast(pp, (int)f), cd = g.bcast(cand, (int)f);
-			const uint32_t m = extend_match<G, ST>(g, in, ip, cd, n - ip);
-			// record the match; emission is deferred (flush_tokens)
-			sts_v2(tok_a + 8 * ntok, next_emit | (ip << 16), cd | (m << 16));
-			if (++ntok == kTokens) {
-				op = flush_tokens<G, ST>(g, dst, op, in, tok_a, ntok);
-				ntok = 0;
-			}
-			next_emit = ip + m;
-			if (next_emit >= ip_limit) {
-				fin = true;
-				break;
-			}
-			// lane of the re-probe position if the parse can stay inside this window
-			const uint32_t nl = uni ? next_emit - wbase : 0x7fffffffu;
-			if (!exact) {
-				// lanes skipped by the copy never insert: undo (ip-1 = lane nl-1 stays, ip = lane nl goes on)
-				if (valid && g.lane > f && g.lane + 1 < nl)
-					sts_u16(slot, old);
-			} else {
-				fhit = f;
-			}
-			if (!multi || nl >= (uint32_t)G) {
-				wbase = next_emit - 1;
-				j0 = -2;
-				t = 1;
-				break;
-			}
-			// continue inside the window: lane nl-1 inserted ip-1, lane nl re-probes, scan restarts at nl+1
-			cur = nl;
-			j0 = -(int)(nl + 1);
-		}
-		if (!fin) {
-			if (exact) {
-				// the table is in its pre-window state: lanes up to the hit insert, the highest lane
-				// of an equal-hash run owns the slot
-				const unsigned I = fhit < 32 ? ((2u << fhit) - 1u) : 0xffffffffu;
-				const unsigned rivals = same & I & ~((2u << g.lane) - 1u);
-				if (valid && ((I >> g.lane) & 1u) && !rivals)
-					sts_u16(slot, pp);
-			}
-			g.sync();
-		}
-		}  // general window
+			}  // general window
 		} while (G == 32 && !fin);  // one group per warp: stay in the window loop until the block is parsed
 		if (fin) {
 			if (ntok)
