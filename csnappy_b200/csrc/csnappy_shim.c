@@ -420,8 +420,12 @@ struct slot {
 	struct buf d_in, d_slots, d_len, d_clen, d_off, d_packed, d_out, d_res, d_ctr;
 	struct buf h_res; /* pinned: [u64 total] or [u32 out_len[n]][i32 status[n]] */
 	struct buf h_in, h_out, h_idx; /* pinned staging of a chunk when the caller's memory is pageable */
-	void *out_dst, *idx_dst;       /* pageable destinations of h_out / h_idx once the chunk's copies have landed */
-	size_t out_n, idx_n;
+	struct {
+		const void *src; /* pinned */
+		void *dst;	 /* the caller's pageable memory */
+		size_t n;
+	} pend[3]; /* copies owed to the caller once the slot's queued device-to-host copies have landed */
+	int npend;
 	uint64_t first;
 	uint32_t n;
 };
@@ -686,19 +690,23 @@ static int is_pageable(const void *p)
 }
 
 /* finish a slot's deferred copy-out: its device-to-host copies into the pinned staging have been queued on b->s */
+static void slot_owe(struct slot *b, const void *pinned_src, void *dst, size_t n)
+{
+	b->pend[b->npend].src = pinned_src;
+	b->pend[b->npend].dst = dst;
+	b->pend[b->npend].n = n;
+	b->npend++;
+}
+
 static int slot_drain(struct slot *b)
 {
-	int e = 0;
-	if (!b->out_n && !b->idx_n)
+	int e = 0, i;
+	if (!b->npend)
 		return 0;
 	e = (int)cudaStreamSynchronize(b->s);
-	if (!e) {
-		if (b->out_n)
-			par_memcpy(b->out_dst, b->h_out.p, b->out_n);
-		if (b->idx_n)
-			memcpy(b->idx_dst, b->h_idx.p, b->idx_n);
-	}
-	b->out_n = b->idx_n = 0;
+	for (i = 0; i < b->npend && !e; i++)
+		par_memcpy(b->pend[i].dst, b->pend[i].src, b->pend[i].n);
+	b->npend = 0;
 	return e;
 }
 
@@ -845,7 +853,7 @@ static void *compress_worker(void *arg)
 			TRY("cudaMallocHost(out)", grow_pin(&b->h_out, (size_t)j->chunk * (j->stored ? j->page : out_stride) + 64));
 			TRY("cudaMallocHost(idx)", grow_pin(&b->h_idx, (size_t)j->chunk * 4 + 64));
 		}
-		b->out_n = b->idx_n = 0;
+		b->npend = 0;
 	}
 	while (retired < n_mine) {
 		if (j->err)
@@ -869,8 +877,7 @@ static void *compress_worker(void *arg)
 				goto out;
 			if (total && j->out_pageable) {
 				TRY("D2H payload", cudaMemcpyAsync(b->h_out.p, b->d_packed.p, total, cudaMemcpyDeviceToHost, b->s));
-				b->out_dst = j->payload_out + pos; /* copied out when the slot comes round again, or at the end */
-				b->out_n = total;
+				slot_owe(b, b->h_out.p, j->payload_out + pos, total); /* copied out when the slot comes round again, or at the end */
 			} else if (total) {
 				TRY("D2H payload", cudaMemcpyAsync(j->payload_out + pos, b->d_packed.p, total, cudaMemcpyDeviceToHost, b->s));
 			}
@@ -916,8 +923,7 @@ static void *compress_worker(void *arg)
 			if (j->index_out && j->out_pageable) {
 				TRY("D2H index", cudaMemcpyAsync(b->h_idx.p, j->stored ? b->d_clen.p : b->d_len.p, (size_t)nb * 4,
 								 cudaMemcpyDeviceToHost, b->s));
-				b->idx_dst = j->index_out + 4 * first;
-				b->idx_n = (size_t)nb * 4;
+				slot_owe(b, b->h_idx.p, j->index_out + 4 * first, (size_t)nb * 4);
 			} else if (j->index_out) {
 				TRY("D2H index", cudaMemcpyAsync(j->index_out + 4 * first, j->stored ? b->d_clen.p : b->d_len.p, (size_t)nb * 4,
 								 cudaMemcpyDeviceToHost, b->s));
@@ -1246,7 +1252,7 @@ int csnappy_batch_compress_fragments_host(const void *h_in, uint64_t in_stride, 
 					  uint32_t n_blocks, void *h_out, uint64_t out_stride,
 					  uint32_t *h_out_len, int workmem_bytes_power_of_two)
 {
-	int rc = 0, k;
+	int rc = 0, k, in_pg, out_pg;
 	size_t chunk, done;
 	struct ctx *c = NULL;
 	if (workmem_bytes_power_of_two < 9 || workmem_bytes_power_of_two > 16)
@@ -1261,18 +1267,32 @@ int csnappy_batch_compress_fragments_host(const void *h_in, uint64_t in_stride, 
 
 	TRY("context", ctx_acquire(&c));
 	chunk = pick_chunk_blocks(in_stride, out_stride, n_blocks);
+	in_pg = is_pageable(h_in);
+	out_pg = is_pageable(h_out) || is_pageable(h_out_len);
 	for (k = 0; k < PIPE; k++) {
 		TRY("cudaMalloc(in)", grow_dev_retry(&c->sl[k].d_in, chunk * in_stride + 64));
 		TRY("cudaMalloc(out)", grow_dev_retry(&c->sl[k].d_slots, chunk * out_stride + 64));
 		TRY("cudaMalloc(len)", grow_dev_retry(&c->sl[k].d_len, chunk * 4 + 64));
 		TRY("cudaMalloc(ctr)", grow_dev_retry(&c->sl[k].d_ctr, 64));
+		if (in_pg)
+			TRY("cudaMallocHost(in)", grow_pin(&c->sl[k].h_in, chunk * in_stride + 64));
+		if (out_pg) {
+			TRY("cudaMallocHost(out)", grow_pin(&c->sl[k].h_out, chunk * out_stride + 64));
+			TRY("cudaMallocHost(len)", grow_pin(&c->sl[k].h_idx, chunk * 8 + 64));
+		}
+		c->sl[k].npend = 0;
 	}
 	for (done = 0, k = 0; done < n_blocks; done += chunk, k = (k + 1) % PIPE) {
 		size_t nb = n_blocks - done < chunk ? n_blocks - done : chunk;
 		struct slot *b = &c->sl[k];
 		struct csb_compress_args a;
-		TRY("H2D", cudaMemcpyAsync(b->d_in.p, (const uint8_t *)h_in + done * in_stride, nb * in_stride,
-					   cudaMemcpyHostToDevice, b->s));
+		const uint8_t *src = (const uint8_t *)h_in + done * in_stride;
+		TRY("copy-out of the slot's previous chunk", slot_drain(b));
+		if (in_pg) { /* pageable caller memory: through the slot's pinned staging (see par_memcpy) */
+			par_memcpy(b->h_in.p, src, nb * in_stride);
+			src = (const uint8_t *)b->h_in.p;
+		}
+		TRY("H2D", cudaMemcpyAsync(b->d_in.p, src, nb * in_stride, cudaMemcpyHostToDevice, b->s));
 		fill_compress_args(&a);
 		a.in = (const uint8_t *)b->d_in.p;
 		a.in_stride = in_stride;
@@ -1284,14 +1304,23 @@ int csnappy_batch_compress_fragments_host(const void *h_in, uint64_t in_stride, 
 		a.wm = workmem_bytes_power_of_two;
 		a.counter = (uint32_t *)b->d_ctr.p;
 		TRY("compress launch", csb_launch_compress(&a, (csb_stream_t)b->s));
-		TRY("D2H data", cudaMemcpyAsync((uint8_t *)h_out + done * out_stride, b->d_slots.p, nb * out_stride,
-						cudaMemcpyDeviceToHost, b->s));
-		TRY("D2H len", cudaMemcpyAsync(h_out_len + done, b->d_len.p, nb * 4, cudaMemcpyDeviceToHost, b->s));
+		if (out_pg) {
+			TRY("D2H data", cudaMemcpyAsync(b->h_out.p, b->d_slots.p, nb * out_stride, cudaMemcpyDeviceToHost, b->s));
+			TRY("D2H len", cudaMemcpyAsync(b->h_idx.p, b->d_len.p, nb * 4, cudaMemcpyDeviceToHost, b->s));
+			slot_owe(b, b->h_out.p, (uint8_t *)h_out + done * out_stride, nb * out_stride);
+			slot_owe(b, b->h_idx.p, h_out_len + done, nb * 4);
+		} else {
+			TRY("D2H data", cudaMemcpyAsync((uint8_t *)h_out + done * out_stride, b->d_slots.p, nb * out_stride,
+							cudaMemcpyDeviceToHost, b->s));
+			TRY("D2H len", cudaMemcpyAsync(h_out_len + done, b->d_len.p, nb * 4, cudaMemcpyDeviceToHost, b->s));
+		}
 	}
 out:
 	if (c)
 		for (k = 0; k < PIPE; k++) {
-			int e = (int)cudaStreamSynchronize(c->sl[k].s);
+			int e = slot_drain(&c->sl[k]);
+			if (!e)
+				e = (int)cudaStreamSynchronize(c->sl[k].s);
 			if (e && !rc)
 				rc = set_err("sync", e);
 		}
@@ -1303,7 +1332,7 @@ int csnappy_batch_decompress_host(const void *h_in, uint64_t in_stride, const ui
 				  uint32_t n_blocks, void *h_out, uint64_t out_stride, uint32_t uniform_out_cap,
 				  uint32_t *h_out_len, int32_t *h_status, uint32_t flags)
 {
-	int rc = 0, k;
+	int rc = 0, k, in_pg, out_pg;
 	size_t chunk, done;
 	struct ctx *c = NULL;
 	if (out_stride < uniform_out_cap)
@@ -1323,11 +1352,20 @@ int csnappy_batch_decompress_host(const void *h_in, uint64_t in_stride, const ui
 
 	TRY("context", ctx_acquire(&c));
 	chunk = pick_chunk_blocks(in_stride, out_stride, n_blocks);
+	in_pg = is_pageable(h_in);
+	out_pg = is_pageable(h_out) || is_pageable(h_out_len) || is_pageable(h_status);
 	for (k = 0; k < PIPE; k++) {
 		TRY("cudaMalloc(in)", grow_dev_retry(&c->sl[k].d_in, chunk * in_stride + 64));
 		TRY("cudaMalloc(out)", grow_dev_retry(&c->sl[k].d_out, chunk * out_stride + 64));
 		TRY("cudaMalloc(aux)", grow_dev_retry(&c->sl[k].d_res, chunk * 12 + 64));
 		TRY("cudaMalloc(ctr)", grow_dev_retry(&c->sl[k].d_ctr, 64));
+		if (in_pg)
+			TRY("cudaMallocHost(in)", grow_pin(&c->sl[k].h_in, chunk * in_stride + 64));
+		if (out_pg) {
+			TRY("cudaMallocHost(out)", grow_pin(&c->sl[k].h_out, chunk * out_stride + 64));
+			TRY("cudaMallocHost(len)", grow_pin(&c->sl[k].h_idx, chunk * 8 + 64));
+		}
+		c->sl[k].npend = 0;
 	}
 	for (done = 0, k = 0; done < n_blocks; done += chunk, k = (k + 1) % PIPE) {
 		size_t nb = n_blocks - done < chunk ? n_blocks - done : chunk;
@@ -1335,8 +1373,13 @@ int csnappy_batch_decompress_host(const void *h_in, uint64_t in_stride, const ui
 		uint32_t *d_ilen = (uint32_t *)b->d_res.p, *d_olen = d_ilen + chunk;
 		int32_t *d_st = (int32_t *)(d_olen + chunk);
 		struct csb_decompress_args a;
-		TRY("H2D", cudaMemcpyAsync(b->d_in.p, (const uint8_t *)h_in + done * in_stride, nb * in_stride,
-					   cudaMemcpyHostToDevice, b->s));
+		const uint8_t *src = (const uint8_t *)h_in + done * in_stride;
+		TRY("copy-out of the slot's previous chunk", slot_drain(b));
+		if (in_pg) {
+			par_memcpy(b->h_in.p, src, nb * in_stride);
+			src = (const uint8_t *)b->h_in.p;
+		}
+		TRY("H2D", cudaMemcpyAsync(b->d_in.p, src, nb * in_stride, cudaMemcpyHostToDevice, b->s));
 		TRY("H2D len", cudaMemcpyAsync(d_ilen, h_in_len + done, nb * 4, cudaMemcpyHostToDevice, b->s));
 		fill_decompress_args(&a);
 		a.in = (const uint8_t *)b->d_in.p;
@@ -1351,15 +1394,27 @@ int csnappy_batch_decompress_host(const void *h_in, uint64_t in_stride, const ui
 		a.flags = flags;
 		a.counter = (uint32_t *)b->d_ctr.p;
 		TRY("decompress launch", csb_launch_decompress(&a, (csb_stream_t)b->s));
-		TRY("D2H data", cudaMemcpyAsync((uint8_t *)h_out + done * out_stride, b->d_out.p, nb * out_stride,
-						cudaMemcpyDeviceToHost, b->s));
-		TRY("D2H len", cudaMemcpyAsync(h_out_len + done, d_olen, nb * 4, cudaMemcpyDeviceToHost, b->s));
-		TRY("D2H status", cudaMemcpyAsync(h_status + done, d_st, nb * 4, cudaMemcpyDeviceToHost, b->s));
+		if (out_pg) {
+			uint8_t *h_len = (uint8_t *)b->h_idx.p, *h_st = h_len + chunk * 4;
+			TRY("D2H data", cudaMemcpyAsync(b->h_out.p, b->d_out.p, nb * out_stride, cudaMemcpyDeviceToHost, b->s));
+			TRY("D2H len", cudaMemcpyAsync(h_len, d_olen, nb * 4, cudaMemcpyDeviceToHost, b->s));
+			TRY("D2H status", cudaMemcpyAsync(h_st, d_st, nb * 4, cudaMemcpyDeviceToHost, b->s));
+			slot_owe(b, b->h_out.p, (uint8_t *)h_out + done * out_stride, nb * out_stride);
+			slot_owe(b, h_len, h_out_len + done, nb * 4);
+			slot_owe(b, h_st, h_status + done, nb * 4);
+		} else {
+			TRY("D2H data", cudaMemcpyAsync((uint8_t *)h_out + done * out_stride, b->d_out.p, nb * out_stride,
+							cudaMemcpyDeviceToHost, b->s));
+			TRY("D2H len", cudaMemcpyAsync(h_out_len + done, d_olen, nb * 4, cudaMemcpyDeviceToHost, b->s));
+			TRY("D2H status", cudaMemcpyAsync(h_status + done, d_st, nb * 4, cudaMemcpyDeviceToHost, b->s));
+		}
 	}
 out:
 	if (c)
 		for (k = 0; k < PIPE; k++) {
-			int e = (int)cudaStreamSynchronize(c->sl[k].s);
+			int e = slot_drain(&c->sl[k]);
+			if (!e)
+				e = (int)cudaStreamSynchronize(c->sl[k].s);
 			if (e && !rc)
 				rc = set_err("sync", e);
 		}

@@ -408,6 +408,45 @@ def test_host_batch_roundtrip(cs, chk):
     assert (st == 0).all() and (blen == 4096).all() and (back == h_in).all()
 
 
+@pytest.mark.parametrize("bounce", [1, 0])
+def test_host_paths_pinned_and_pageable_agree(cs, chk, bounce):
+    """The host-buffer pipelines take pinned caller memory as it is and stage pageable memory through their own pinned
+    slot buffers (copy threads; bounce=0: the round-1 behaviour, pageable memory straight into cudaMemcpyAsync):
+    same bytes either way, for the strided batch calls and for the page container, over several chunks per slot."""
+    pages = fuzz_pages(77, 3000, 4096) * 12  # 36000 pages: 5-6 chunks, so every pipeline slot is reused
+    B = len(pages)
+    flat = np.frombuffer(b"".join(pages), dtype=np.uint8)
+    ostride = cs.api.out_stride_for(4096)
+    cs.set_tuning("no_bounce", 0 if bounce else 1)
+    try:
+        res = {}
+        for kind in ("pageable", "pinned"):
+            mk = (lambda n, dt=torch.uint8: torch.zeros(n, dtype=dt).pin_memory()) if kind == "pinned" else \
+                 (lambda n, dt=torch.uint8: torch.zeros(n, dtype=dt))
+            h_in = mk(B * 4096)
+            h_in.copy_(torch.from_numpy(flat.copy()))
+            assert h_in.is_pinned() == (kind == "pinned")
+            h_out, h_len = mk(B * ostride), mk(B, torch.int32)
+            cs.batch_compress_fragments_host(h_in, 4096, B, 13, h_out, h_len)
+            back, blen, st = mk(B * 4096), mk(B, torch.int32), mk(B, torch.int32)
+            cs.batch_decompress_host(h_out, ostride, h_len, B, back, 4096, 4096, blen, st)
+            assert int((st != 0).sum()) == 0 and int((blen != 4096).sum()) == 0 and torch.equal(back, h_in), kind
+            cont = mk(cs.api.bc_max_container_length(B * 4096, 4096))
+            clen = cs.api.bc_compress_host(h_in, B * 4096, cont, 13, 4096)
+            back2 = mk(B * 4096)
+            assert cs.api.bc_decompress_host(cont, clen, back2, 4096) == (0, B * 4096, None)
+            assert torch.equal(back2, h_in), kind
+            lens = h_len.numpy().astype(np.uint32)
+            res[kind] = (lens.copy(), h_out.numpy().reshape(B, ostride)[np.arange(0, B, 41)].copy(), cont[:clen].numpy().copy())
+        assert (res["pageable"][0] == res["pinned"][0]).all()
+        for i, k in enumerate(range(0, B, 41)):
+            n = res["pinned"][0][k]
+            assert res["pageable"][1][i, :n].tobytes() == res["pinned"][1][i, :n].tobytes() == chk.compress_fragment(pages[k], 13), k
+        assert res["pageable"][2].tobytes() == res["pinned"][2].tobytes()
+    finally:
+        cs.set_tuning("no_bounce", 0)
+
+
 def test_scale_mixed_pages_roundtrip_and_oracle_sample(cs, chk):
     """256 Ki mixed 4 KiB pages (1 GiB): round trip on the device, oracle check of a sample,
     and the checksum-of-lengths property against the CPU harness on a 16 Ki page prefix."""
