@@ -410,7 +410,7 @@ def main():
     # The call a block_compressor / zram style user makes: pages in host memory -> the page container
     # (block_compressor.c:275-345) in host memory, and back (block_compressor.c:347-394).  Every step
     # copies all pages H2D, the container D2H, the container H2D and all pages D2H inside the timed region.
-    e2e_ms = e2e_pageable_ms = None
+    e2e_ms = e2e_pageable_ms = e2e_both_ms = None
     h2d = d2h = 0
     if not args.no_e2e:
         h_in = torch.empty(B * PAGE, dtype=torch.uint8, pin_memory=True)
@@ -443,6 +443,32 @@ def main():
         payload = clen_box[0] - 4 - 4 * B
         h2d = B * PAGE + payload + 4 * B
         d2h = payload + 4 * B + 8 * ((B + 8191) // 8192) + B * PAGE + 8 * B
+        # both directions of the bus at once: one thread compresses the batch while another decompresses the
+        # container of the previous step (the calls are re-entrant; a zram-like user runs both all the time).
+        # Same work per step as `e2e`, but H2D and D2H are balanced instead of 4.3 GB one way + 2.4 GB the other.
+        import threading
+
+        h_cont2 = torch.empty(h_cont.numel(), dtype=torch.uint8, pin_memory=True)
+
+        def both_step():
+            def comp():
+                assert cs.api.bc_compress_host(h_in, B * PAGE, h_cont2, WM, PAGE) == clen_box[0]
+
+            t = threading.Thread(target=comp)
+            t.start()
+            rc, olen, _ = cs.api.bc_decompress_host(h_cont, clen_box[0], h_back, PAGE)
+            t.join()
+            assert rc == 0 and olen == B * PAGE
+
+        both_step()
+        barrier()
+        w0 = time.perf_counter()
+        for _ in range(3):
+            both_step()
+        torch.cuda.synchronize()
+        e2e_both_ms = 1e3 * (time.perf_counter() - w0) / 3
+        assert torch.equal(h_cont2[: clen_box[0]], h_cont[: clen_box[0]]) and torch.equal(h_back, h_in)
+        del h_cont2
         # the same calls on ordinary pageable caller memory (what a caller that never heard of CUDA passes in)
         p_in, p_back = h_in.clone(memory_format=torch.contiguous_format), torch.empty(B * PAGE, dtype=torch.uint8)
         p_cont = torch.empty(h_cont.numel(), dtype=torch.uint8)
@@ -518,12 +544,12 @@ def main():
         workloads = run_workloads(args, cs, synth, dev, rank, world, barrier)
 
     # ---- reduce over ranks: max time, sum bytes -------------------------------------------
-    vals = torch.tensor([elapsed_ms, tc_ms, td_ms, e2e_ms or 0.0, e2e_pageable_ms or 0.0], dtype=torch.float64, device=dev)
+    vals = torch.tensor([elapsed_ms, tc_ms, td_ms, e2e_ms or 0.0, e2e_pageable_ms or 0.0, e2e_both_ms or 0.0], dtype=torch.float64, device=dev)
     sums = torch.tensor([float(B * PAGE), float(csum), float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    elapsed_ms, tc_ms, td_ms, e2e_max, e2e_pageable_max = vals.tolist()
+    elapsed_ms, tc_ms, td_ms, e2e_max, e2e_pageable_max, e2e_both_max = vals.tolist()
     total_n, total_c, total_launches = sums.tolist()
 
     if rank == 0:
@@ -572,6 +598,11 @@ def main():
                            "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
                            "ms_per_step": round(e2e_max, 2),
                            "api": "csnappy_bc_compress_host + csnappy_bc_decompress_host (block_compressor page container), pinned host buffers"}
+        if e2e_both_max:
+            line["e2e_concurrent"] = {"value": round(2 * total_n / (e2e_both_max * 1e-3) / 1e9, 2), "unit": "GB/s",
+                                      "ms_per_step": round(e2e_both_max, 2),
+                                      "api": "csnappy_bc_compress_host of the batch and csnappy_bc_decompress_host of the previous "
+                                             "container running in two threads at once (pinned buffers): both PCIe directions busy"}
         if e2e_pageable_max:
             line["e2e_pageable"] = {"value": round(2 * total_n / (e2e_pageable_max * 1e-3) / 1e9, 2), "unit": "GB/s",
                                     "ms_per_step": round(e2e_pageable_max, 2),

@@ -46,7 +46,7 @@ def test_b200_arm_line_on_gpu():
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] > 32768 * 4096 and e["d2h_bytes_per_step"] > 32768 * 4096
     assert e["value"] < d["value"]  # host buffers and PCIe inside the timed region
-    assert 0 < d["e2e_pageable"]["value"] < d["value"]
+    assert 0 < d["e2e_pageable"]["value"] < d["value"] and 0 < d["e2e_concurrent"]["value"] < d["value"]
     # BASELINE.json configs[2] / [3] ride in the same line
     w = d["workloads"]
     for wm in ("wm15", "wm16"):
