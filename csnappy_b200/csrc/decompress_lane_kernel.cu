@@ -121,17 +121,24 @@ __device__ __forceinline__ void ring_fetch(uint32_t ring, uintptr_t line)
 	for (uint32_t i = 0; i < kLine; i += 16)
 		cp_async16(d + i, line + i);
 }
-// Keep the ring's invariant for read position g: the line holding g and the kAhead behind it are requested (lines
-// that start at or past `lim` hold no input byte and are never touched).  `have` = line of the previous read
-// position.  Returns true after a jump (new block, bulk literal): those lines are needed at once.
-__device__ __forceinline__ bool ring_ensure(uint32_t ring, uintptr_t g, uintptr_t lim, uintptr_t &have)
+// The ring's invariant for read position g: the line holding g and the kAhead behind it are requested (lines that
+// start at or past `lim` hold no input byte and are never touched).  `have` = line of the previous read position.
+// ring_kind: 0 = nothing to do, 1 = the position entered the next line (request one line ahead), 2 = a jump (new block,
+// behind a bulk literal): every line is new and needed at once.  cp.async operations are NOT ordered among themselves,
+// so before a jump refills the slots nothing may still be in flight towards them: the caller drains (wait_group 0)
+// between ring_kind and ring_request whenever a lane of the warp jumps.
+__device__ __forceinline__ uint32_t ring_kind(uintptr_t g, uintptr_t lim, uintptr_t have)
 {
 	const uintptr_t cur = g & ~(uintptr_t)(kLine - 1);
 	if (cur == have || cur >= lim)
-		return false;
-	const bool jump = cur != have + kLine;
+		return 0;
+	return cur == have + kLine ? 1u : 2u;
+}
+__device__ __forceinline__ void ring_request(uint32_t ring, uintptr_t g, uintptr_t lim, uintptr_t &have, uint32_t kind)
+{
+	const uintptr_t cur = g & ~(uintptr_t)(kLine - 1);
 	have = cur;
-	if (jump) {
+	if (kind == 2) {
 #pragma unroll
 		for (uint32_t i = 0; i < kAhead; ++i)
 			if (cur + i * kLine < lim)
@@ -139,7 +146,6 @@ __device__ __forceinline__ bool ring_ensure(uint32_t ring, uintptr_t g, uintptr_
 	}
 	if (cur + kAhead * kLine < lim)
 		ring_fetch(ring, cur + kAhead * kLine);
-	return jump;
 }
 // `need` (1..16) bytes at global byte address g out of the ring, little endian
 __device__ __forceinline__ U128 ring_load16(uint32_t ring, uintptr_t g, uint32_t need)
@@ -193,7 +199,6 @@ __global__ void __launch_bounds__(kLaneThreads) decompress_lane_kernel(const Lan
 	extern __shared__ __align__(128) uint8_t lane_smem[];
 	const uint32_t ring = smem_u32(lane_smem) + threadIdx.x * kRing;
 	uintptr_t have_line = 1;  // never a line address
-	bool fresh = false;       // lines were requested that the next step needs
 
 	for (;;) {
 		// ---- CLAIM ----
@@ -245,12 +250,15 @@ __global__ void __launch_bounds__(kLaneThreads) decompress_lane_kernel(const Lan
 			}
 		}
 		// ---- INPUT RING: request what the new read position needs; wait for what this step reads ----
-		if (have)
-			fresh |= ring_ensure(ring, src + ip, src_end, have_line);
+		const uint32_t kind = have ? ring_kind(src + ip, src_end, have_line) : 0u;
+		const bool jump = __any_sync(full, kind == 2u);
+		if (jump)
+			asm volatile("cp.async.wait_group 0;" ::: "memory");  // drain before any slot is refilled
+		if (kind)
+			ring_request(ring, src + ip, src_end, have_line, kind);
 		asm volatile("cp.async.commit_group;" ::: "memory");
-		if (__any_sync(full, fresh)) {
+		if (jump) {
 			asm volatile("cp.async.wait_group 0;" ::: "memory");
-			fresh = false;
 		} else {
 			if (kAhead >= 3)
 				asm volatile("cp.async.wait_group 2;" ::: "memory");

@@ -447,6 +447,48 @@ def test_host_paths_pinned_and_pageable_agree(cs, chk, bounce):
         cs.set_tuning("no_bounce", 0)
 
 
+def test_lane_decoder_blocks_after_failed_blocks_in_the_same_lane(cs, chk, urls):
+    """Lane-per-block decoder with few lanes (one warp per SM), so every lane decodes ~10 blocks one after the other:
+    a block that fails half-way leaves a line of its input in flight towards the lane's shared-memory ring; the next
+    block of that lane must not see it (cp.async operations are unordered: the ring is drained before a refill)."""
+    rng = np.random.default_rng(99)
+    pages = [urls[o:o + 4096] for o in range(0, 4096 * 160, 4096)]
+    comp = [chk.compress_fragment(p, 13) for p in pages]
+    streams, caps = [], []
+    for i in range(48000):
+        c = bytearray(comp[i % len(comp)])
+        k = int(rng.integers(0, 4))
+        if k == 1:  # an invalid copy somewhere behind the first lines: offset far beyond what was produced
+            at = int(rng.integers(70, len(c) - 8))
+            c[at:at + 3] = bytes([0xFE, 0xFF, 0xFF])
+        elif k == 2:  # output capacity too small
+            pass
+        streams.append(bytes(c))
+        caps.append(4096 if k != 2 else int(rng.integers(100, 3000)))
+    stride = (cs.csnappy_max_compressed_length(4096) + 15) // 16 * 16
+    d_in, d_len, _, _ = _to_dev(streams, stride)
+    d_caps = torch.tensor(caps, dtype=torch.int32).cuda()
+    cs.set_tuning("decompress_stage_input", 4)
+    cs.set_tuning("decompress_lane_warps", 1)
+    try:
+        out, out_len, status = cs.batch_decompress(d_in, d_len, len(streams), 4096, in_stride=stride, out_caps=d_caps,
+                                                   out_stride=4096)
+        torch.cuda.synchronize()
+    finally:
+        cs.set_tuning("decompress_stage_input", 0)
+        cs.set_tuning("decompress_lane_warps", 0)
+    st, ol, o = status.cpu().numpy(), out_len.cpu().numpy(), out.cpu().numpy().reshape(len(streams), 4096)
+    memo = {}
+    for i, s in enumerate(streams):
+        key = (s, caps[i])
+        if key not in memo:
+            memo[key] = oracle.port().decompress_noheader(s, caps[i])
+        rc, exp = memo[key]
+        assert st[i] == rc, (i, int(st[i]), rc)
+        if rc == 0:
+            assert ol[i] == len(exp) and o[i, : ol[i]].tobytes() == exp, i
+
+
 def test_scale_mixed_pages_roundtrip_and_oracle_sample(cs, chk):
     """256 Ki mixed 4 KiB pages (1 GiB): round trip on the device, oracle check of a sample,
     and the checksum-of-lengths property against the CPU harness on a 16 Ki page prefix."""

@@ -30,6 +30,14 @@ for lanes in (32, 16, 8):
     back2, _, st2 = cs.batch_decompress(packed, out_len, B, L, in_off=off[:-1].contiguous())
     torch.cuda.synchronize()
     assert int((st2 != 0).sum()) == 0 and torch.equal(back2.view(B, L), pages.view(B, L)), lanes
+# compress reading the block from global memory (the form large fragments take in large batches)
+cs.set_tuning("compress_lanes", 0)
+cs.set_tuning("compress_stage_input", 2)
+out_u, out_len_u = cs.batch_compress_fragments(pages, L, B, 13)
+cs.set_tuning("compress_stage_input", 0)
+out_s, out_len_s = cs.batch_compress_fragments(pages, L, B, 13)
+torch.cuda.synchronize()
+assert torch.equal(out_len_u, out_len_s)
 # the other decoder families on the same batch: 3 = warp per block against global memory, 4 = lane per block
 cs.set_tuning("compress_lanes", 0)
 cs.set_tuning("decompress_lanes", 0)
