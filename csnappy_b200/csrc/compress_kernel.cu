@@ -688,15 +688,16 @@ extern "C" int csb_launch_compress(const struct csb_compress_args *a, csb_stream
 		budget = di.smem_per_block_optin;
 	int groups = (int)(budget / p.group_smem);
 	const int max_groups = kMaxThreads / G;
-	// Blocks of which fewer than 8 fit an SM staged (fragments above ~14 KB with their table) are read from global
-	// memory instead: only the table stays in shared memory and about twice as many chains run per SM
-	// (32 KiB / wm 15: 7 instead of 3).  stage_input: 0 = this rule, 1 = always stage, 2 = never stage.
+	// Blocks of which fewer than 8 fit an SM staged are read from global memory instead when that at least doubles the
+	// chains per SM (32 KiB / wm 15: 7 instead of 3, 14.7 -> 20 GB/s; an unstaged chain runs at ~57 % of a staged one, so
+	// 3 instead of 2 at wm 16 or 13 instead of 7 at 16 KiB / wm 14 do not pay).  stage_input: 0 = this rule, 1 = always
+	// stage, 2 = never stage.
 	bool staged = true;
 	if (G == 32 && a->stage_input != 1) {
 		const uint32_t lean = p.table_bytes + 16 + 8 * kTokens;
 		const int lean_groups = (int)(budget / lean) < max_groups ? (int)(budget / lean) : max_groups;
 		// (a batch that fits the staged slots of the machine in one go gains nothing from more slots)
-		if (a->stage_input == 2 || (groups < 8 && lean_groups > groups && a->n_blocks > (uint32_t)(di.sm_count * (groups > 0 ? groups : 1)))) {
+		if (a->stage_input == 2 || (groups < 8 && lean_groups >= 2 * groups && a->n_blocks > (uint32_t)(di.sm_count * (groups > 0 ? groups : 1)))) {
 			staged = false;
 			p.in_area = 0;
 			p.group_smem = lean;
