@@ -443,46 +443,48 @@ def main():
         payload = clen_box[0] - 4 - 4 * B
         h2d = B * PAGE + payload + 4 * B
         d2h = payload + 4 * B + 8 * ((B + 8191) // 8192) + B * PAGE + 8 * B
-        # both directions of the bus at once: one thread compresses the batch while another decompresses the
-        # container of the previous step (the calls are re-entrant; a zram-like user runs both all the time).
-        # Same work per step as `e2e`, but H2D and D2H are balanced instead of 4.3 GB one way + 2.4 GB the other.
-        import threading
+        if world == 1:  # single-GPU runs only: the extra host buffers and copy threads of 8 ranks would fight over one host
+            # both directions of the bus at once: one thread compresses the batch while another decompresses the
+            # container of the previous step (the calls are re-entrant; a zram-like user runs both all the time).
+            # Same work per step as `e2e`, but H2D and D2H are balanced instead of 4.3 GB one way + 2.4 GB the other.
+            import threading
 
-        h_cont2 = torch.empty(h_cont.numel(), dtype=torch.uint8, pin_memory=True)
+            h_cont2 = torch.empty(h_cont.numel(), dtype=torch.uint8, pin_memory=True)
 
-        def both_step():
-            def comp():
-                assert cs.api.bc_compress_host(h_in, B * PAGE, h_cont2, WM, PAGE) == clen_box[0]
+            def both_step():
+                def comp():
+                    assert cs.api.bc_compress_host(h_in, B * PAGE, h_cont2, WM, PAGE) == clen_box[0]
 
-            t = threading.Thread(target=comp)
-            t.start()
-            rc, olen, _ = cs.api.bc_decompress_host(h_cont, clen_box[0], h_back, PAGE)
-            t.join()
-            assert rc == 0 and olen == B * PAGE
+                t = threading.Thread(target=comp)
+                t.start()
+                rc, olen, _ = cs.api.bc_decompress_host(h_cont, clen_box[0], h_back, PAGE)
+                t.join()
+                assert rc == 0 and olen == B * PAGE
 
-        both_step()
-        barrier()
-        w0 = time.perf_counter()
-        for _ in range(3):
             both_step()
-        torch.cuda.synchronize()
-        e2e_both_ms = 1e3 * (time.perf_counter() - w0) / 3
-        assert torch.equal(h_cont2[: clen_box[0]], h_cont[: clen_box[0]]) and torch.equal(h_back, h_in)
-        del h_cont2
-        # the same calls on ordinary pageable caller memory (what a caller that never heard of CUDA passes in)
-        p_in, p_back = h_in.clone(memory_format=torch.contiguous_format), torch.empty(B * PAGE, dtype=torch.uint8)
-        p_cont = torch.empty(h_cont.numel(), dtype=torch.uint8)
-        assert not p_in.is_pinned() and not p_cont.is_pinned()
-        h_in, h_cont, h_back = p_in, p_cont, p_back
-        e2e_step()
-        assert torch.equal(h_back, h_in), "pageable e2e round trip mismatch"
-        barrier()
-        w0 = time.perf_counter()
-        for _ in range(2):
+            barrier()
+            w0 = time.perf_counter()
+            for _ in range(3):
+                both_step()
+            torch.cuda.synchronize()
+            e2e_both_ms = 1e3 * (time.perf_counter() - w0) / 3
+            assert torch.equal(h_cont2[: clen_box[0]], h_cont[: clen_box[0]]) and torch.equal(h_back, h_in)
+            del h_cont2
+            # the same calls on ordinary pageable caller memory (what a caller that never heard of CUDA passes in)
+            p_in, p_back = h_in.clone(memory_format=torch.contiguous_format), torch.empty(B * PAGE, dtype=torch.uint8)
+            p_cont = torch.empty(h_cont.numel(), dtype=torch.uint8)
+            assert not p_in.is_pinned() and not p_cont.is_pinned()
+            h_in, h_cont, h_back = p_in, p_cont, p_back
             e2e_step()
-        torch.cuda.synchronize()
-        e2e_pageable_ms = 1e3 * (time.perf_counter() - w0) / 2
-        del h_in, h_cont, h_back, p_in, p_cont, p_back
+            assert torch.equal(h_back, h_in), "pageable e2e round trip mismatch"
+            barrier()
+            w0 = time.perf_counter()
+            for _ in range(2):
+                e2e_step()
+            torch.cuda.synchronize()
+            e2e_pageable_ms = 1e3 * (time.perf_counter() - w0) / 2
+            del p_in, p_cont, p_back
+        del h_in, h_cont, h_back
 
     # ---- short diagnostic runs (device-resident, rank 0's times): the alternative text class of SURVEY 8d, and
     # ---- every page class of the main workload on its own ("report per-class and mixed") ----------
