@@ -32,6 +32,8 @@
 //     memory instead (Input<false>): only the table stays in shared memory, 7 chains per SM.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "device_common.cuh"
 #include "kernels.h"
 
@@ -394,13 +396,26 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 			// and the window is CUT in front of the first lane that has a lower partner: the lanes before it are
 			// conflict-free, the lanes from it on take their inserts back and are probed again by the next window.
 			// Three or more lanes on one slot restore the table and hand the window to the general code below.
-			bool done_fast = false;
-			if (G == 32 && j0 < 24) {
-				uint32_t cut = j0 > 0 ? 32u - (uint32_t)j0 : 32u;
-				const uint32_t pp = wbase + g.lane;
-				bool valid = pp < ip_limit && g.lane < cut;
-				// invalid lanes read on inside the staging pad (pp + 3 <= n + 19) and never store
-				const uint32_t bytes = in.u32(pp);
+			// A STRIDED window (UNI = false: probe indices from 32 on, strides 2, 3, ... -- the second and later
+			// windows of a scan that found nothing) takes the same front end and the same cut; it holds one copy at
+			// most, positions come from the lanes by shuffle, and lanes are compared through their positions.
+			auto fast_window = [&](auto uni_c) -> bool {
+				constexpr bool UNI = decltype(uni_c)::value;
+				uint32_t cut, pp, s;
+				if constexpr (UNI) {
+					cut = j0 > 0 ? 32u - (uint32_t)j0 : 32u;
+					pp = wbase + g.lane;
+					s = 1;
+				} else {
+					const uint32_t s0 = (32u + j0) >> 5;
+					const int jb = ((j0 >> 5) + 1) << 5;  // first probe index with stride s0 + 1
+					cut = 32u;
+					pp = wbase + g.lane * s0 + max(j0 + (int)g.lane - jb, 0);
+					s = (32u + j0 + g.lane) >> 5;
+				}
+				bool valid = pp + s <= ip_limit && g.lane < cut;
+				// consecutive positions: invalid lanes read on inside the staging pad (pp + 3 <= n + 19) and never store
+				const uint32_t bytes = in.u32(UNI || valid ? pp : 0u);
 				const uint32_t slot = tab_a + 2 * ((bytes * kHashMul) >> shift);
 				const uint32_t old = lds_u16(slot);
 				g.sync();
@@ -411,7 +426,6 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 				const uint32_t cand = valid ? old : 0u;  // (blocks under 15 bytes never clear the table)
 				const uint32_t cb = in.u32(cand);
 				const bool lost = valid && rb1 != pp;
-				done_fast = true;
 				if (g.ballot(lost)) {
 					g.sync();
 					if (lost)
@@ -423,69 +437,84 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 					if (triple) {
 						if (valid)
 							sts_u16(slot, old);
-						done_fast = false;
-					} else {
-						const uint32_t q = lost ? rb1 : rb2;  // the partner's position (own position: none)
-						const bool hasp = valid && q != pp;
-						const uint32_t pl = q - wbase;
-						cut = __ffs(g.ballot(hasp && q < pp)) - 1;  // first lane with a lower partner (there is one)
-						const bool upper = g.lane >= cut;
-						// lanes from the cut on leave the table as if they had never inserted; a lane in front of the
-						// cut whose partner is behind it owns the slot again
-						const bool wr_old = valid && upper && (!hasp || (pl >= cut && g.lane < pl));
-						const bool wr_pp = valid && !upper && hasp;
-						if (wr_old || wr_pp)
-							sts_u16(slot, wr_pp ? pp : old);
-						valid = valid && !upper;
+						g.sync();
+						return false;
 					}
+					const uint32_t q = lost ? rb1 : rb2;  // the partner's position (own position: none)
+					const bool hasp = valid && q != pp;
+					cut = __ffs(g.ballot(hasp && q < pp)) - 1;  // first lane with a lower partner (there is one)
+					const uint32_t pcut = UNI ? wbase + cut : g.bcast(pp, (int)cut);  // its position
+					const bool upper = g.lane >= cut;
+					// lanes from the cut on leave the table as if they had never inserted; a lane in front of the
+					// cut whose partner is behind it owns the slot again
+					const bool wr_old = valid && upper && (!hasp || (q >= pcut && pp < q));
+					const bool wr_pp = valid && !upper && hasp;
+					if (wr_old || wr_pp)
+						sts_u16(slot, wr_pp ? pp : old);
+					valid = valid && !upper;
 					g.sync();
 				}
-				if (done_fast) {
-					const unsigned H = g.ballot(valid && cb == bytes);
-					const bool all_valid = wbase + cut - 1 < ip_limit;
-					uint32_t cur = t;
-					for (;;) {
-						const unsigned elig = H & (0xffffffffu << cur);
-						if (!elig) {
-							if (!all_valid) {
-								fin = true;  // ran into ip_limit without a hit
-							} else {
+				const unsigned H = g.ballot(valid && cb == bytes);
+				bool all_valid;
+				if constexpr (UNI)
+					all_valid = wbase + cut - 1 < ip_limit;
+				else
+					all_valid = g.ballot(valid) == (cut >= 32u ? 0xffffffffu : (1u << cut) - 1u);
+				uint32_t cur = t;
+				for (;;) {
+					const unsigned elig = H & (0xffffffffu << cur);
+					if (!elig) {
+						if (!all_valid) {
+							fin = true;  // ran into ip_limit without a hit
+						} else {
+							if constexpr (UNI)
 								wbase += cut;
-								j0 += (int)cut;
-								t = 0;
-							}
-							break;
+							else  // position of the probe behind the last one of this window
+								wbase = cut < 32u ? g.bcast(pp, (int)cut) : g.bcast(pp + s, 31);
+							j0 += (int)cut;
+							t = 0;
 						}
-						const uint32_t f = __ffs(elig) - 1;
-						const uint32_t ip = wbase + f, cd = g.bcast(cand, (int)f);
-						const uint32_t m = extend_match<G, ST>(g, in, ip, cd, n - ip);
-						sts_v2(tok_a + 8 * ntok, next_emit | (ip << 16), cd | (m << 16));
-						if (++ntok == kTokens) {
-							op = flush_tokens<G, ST>(g, dst, op, in, tok_a, ntok);
-							ntok = 0;
-						}
-						next_emit = ip + m;
-						if (next_emit >= ip_limit) {
-							fin = true;
-							break;
-						}
-						const uint32_t nl = next_emit - wbase;  // lane of the re-probe position
-						// lanes skipped by the copy never insert: undo (ip-1 = lane nl-1 stays, ip = lane nl goes on)
-						if (valid && g.lane > f && g.lane + 1 < nl)
-							sts_u16(slot, old);
-						if (nl >= cut) {
-							wbase = next_emit - 1;
-							j0 = -2;
-							t = 1;
-							break;
-						}
+						break;
+					}
+					const uint32_t f = __ffs(elig) - 1;
+					const uint32_t ip = UNI ? wbase + f : g.bcast(pp, (int)f), cd = g.bcast(cand, (int)f);
+					const uint32_t m = extend_match<G, ST>(g, in, ip, cd, n - ip);
+					sts_v2(tok_a + 8 * ntok, next_emit | (ip << 16), cd | (m << 16));
+					if (++ntok == kTokens) {
+						op = flush_tokens<G, ST>(g, dst, op, in, tok_a, ntok);
+						ntok = 0;
+					}
+					next_emit = ip + m;
+					if (next_emit >= ip_limit) {
+						fin = true;
+						break;
+					}
+					// lane of the re-probe position if the parse can stay inside this window
+					const uint32_t nl = UNI ? next_emit - wbase : 0x7fffffffu;
+					// lanes skipped by the copy never insert: undo (ip-1 = lane nl-1 stays, ip = lane nl goes on)
+					if (valid && g.lane > f && g.lane + 1 < nl)
+						sts_u16(slot, old);
+					bool stay = false;
+					if constexpr (UNI)
+						stay = nl < cut;
+					if (!stay) {
+						wbase = next_emit - 1;
+						j0 = -2;
+						t = 1;
+						break;
+					}
+					if constexpr (UNI) {
 						cur = nl;
 						j0 = -(int)(nl + 1);
 					}
-					if (!fin)
-						g.sync();
 				}
-			}
+				if (!fin)
+					g.sync();
+				return true;
+			};
+			bool done_fast = false;
+			if (G == 32)
+				done_fast = j0 < 24 ? fast_window(std::true_type{}) : fast_window(std::false_type{});
 			if (!done_fast) {
 				// ---- one WINDOW of G probe positions (csnappy_compress.c:535-552 and 587-593) ----
 				// Lane k probes the k-th position of the window.  j0 + k is that probe's index in the
