@@ -42,7 +42,6 @@ namespace csb {
 constexpr uint32_t kInPad = 48;	     // staging shift (< 16) + slack after the input for over-reads of the match extension
 constexpr uint32_t kTailMargin = 15; // kInputMarginBytes, csnappy_compress.c:468
 constexpr int kMaxThreads = 640;
-constexpr uint32_t kTokens = 32;     // deferred (literal, copy) tokens per group before a flush
 
 struct CompressParams {
 	csb_compress_args a;
@@ -50,7 +49,7 @@ struct CompressParams {
 	uint32_t table_bytes;  // 1 << wm
 	uint32_t in_cap;       // longest block the staging area holds (<= 32768)
 	uint32_t in_area;      // bytes reserved for the staged input incl. pad (multiple of 16)
-	uint32_t group_smem;   // table_bytes + in_area + 16 (mbarrier) + 8 * kTokens
+	uint32_t group_smem;   // table_bytes + in_area + 16 (mbarrier)
 	uint32_t groups;       // groups per CTA that own shared memory
 };
 
@@ -189,22 +188,22 @@ __device__ __forceinline__ uint32_t emit_copy(const Group<G> &g, uint8_t *dst, u
 }
 
 // ---- deferred emission ------------------------------------------------------------------------
-// The parse only records a token per match -- (next_emit | ip << 16, candidate | length << 16) --
-// and every kTokens matches the group emits them together: sizes in parallel, output offsets by a
-// shuffle scan, then every lane writes ITS token (literal header + payload + copy tag) on its own.
+// The parse only records a token per match -- (next_emit | ip << 16, candidate | length << 16), token k of
+// a batch in the registers of lane k -- and every G matches the group emits them together: sizes in parallel,
+// output offsets by a shuffle scan, then every lane writes ITS token (literal header + payload + copy tag).
 // That replaces ~30 warp instructions per match in the serial chain by ~6 amortised ones.  Tokens
 // with a literal over 32 bytes or a copy over 64 bytes are written by the whole group instead.
 template <int G, bool ST>
 __device__ __forceinline__ uint32_t flush_tokens(const Group<G> &g, uint8_t *dst, uint32_t op, const Input<ST> &in,
-						 uint32_t tok_a, uint32_t count)
+						 uint32_t count, uint32_t tx, uint32_t ty)
 {
 	g.sync();
-	for (uint32_t base = 0; base < count; base += G) {
-		const uint32_t k = base + g.lane;
+	{
+		const uint32_t k = g.lane;
 		const bool have = k < count;
 		uint32_t ne = 0, litlen = 0, off = 1, m = 4;
 		if (have) {
-			const uint2 t = lds_v2(tok_a + 8 * k);
+			const uint2 t = make_uint2(tx, ty);  // token k lives in lane k (one batch = G tokens)
 			ne = t.x & 0xffffu;
 			litlen = (t.x >> 16) - ne;
 			off = (t.x >> 16) - (t.y & 0xffffu);
@@ -303,7 +302,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 	uint8_t *sarea = gs + p.table_bytes;  // staged input, 16-byte aligned
 	const uint32_t sarea_a = smem_u32(sarea), tab_a = smem_u32(tab);
 	Input<ST> in;  // staged: sarea_a + (src & 15), the shared address where the block's first byte lands
-	const uint32_t bar = smem_u32(sarea + p.in_area), tok_a = bar + 16;
+	const uint32_t bar = smem_u32(sarea + p.in_area);
 	const unsigned full = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
 
 	if (g.lane == 0) {
@@ -316,6 +315,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 	uint32_t parity = 0;
 	// per-block state
 	uint32_t blk = 0, n = 0, ip_limit = 0, op = 0, next_emit = 0, wbase = 1, t = 0, ntok = 0;
+	uint32_t tx = 0, ty = 0;  // this lane's token of the current batch (token k of a batch lives in lane k)
 	int shift = 0, j0 = 0;
 	uint8_t *dst = nullptr;
 
@@ -479,9 +479,12 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 					const uint32_t f = __ffs(elig) - 1;
 					const uint32_t ip = UNI ? wbase + f : g.bcast(pp, (int)f), cd = g.bcast(cand, (int)f);
 					const uint32_t m = extend_match<G, ST>(g, in, ip, cd, n - ip);
-					sts_v2(tok_a + 8 * ntok, next_emit | (ip << 16), cd | (m << 16));
-					if (++ntok == kTokens) {
-						op = flush_tokens<G, ST>(g, dst, op, in, tok_a, ntok);
+					if (g.lane == ntok) {
+						tx = next_emit | (ip << 16);
+						ty = cd | (m << 16);
+					}
+					if (++ntok == (uint32_t)G) {
+						op = flush_tokens<G, ST>(g, dst, op, in, ntok, tx, ty);
 						ntok = 0;
 					}
 					next_emit = ip + m;
@@ -612,9 +615,12 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 					const uint32_t ip = g.bcast(pp, (int)f), cd = g.bcast(cand, (int)f);
 					const uint32_t m = extend_match<G, ST>(g, in, ip, cd, n - ip);
 					// record the match; emission is deferred (flush_tokens)
-					sts_v2(tok_a + 8 * ntok, next_emit | (ip << 16), cd | (m << 16));
-					if (++ntok == kTokens) {
-						op = flush_tokens<G, ST>(g, dst, op, in, tok_a, ntok);
+					if (g.lane == ntok) {
+						tx = next_emit | (ip << 16);
+						ty = cd | (m << 16);
+					}
+					if (++ntok == (uint32_t)G) {
+						op = flush_tokens<G, ST>(g, dst, op, in, ntok, tx, ty);
 						ntok = 0;
 					}
 					next_emit = ip + m;
@@ -656,7 +662,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 		} while (G == 32 && !fin);  // one group per warp: stay in the window loop until the block is parsed
 		if (fin) {
 			if (ntok)
-				op = flush_tokens<G, ST>(g, dst, op, in, tok_a, ntok);
+				op = flush_tokens<G, ST>(g, dst, op, in, ntok, tx, ty);
 			ntok = 0;
 			if (next_emit < n)
 				op += emit_literal<G, ST>(g, dst + op, in, next_emit, n - next_emit);
@@ -707,7 +713,7 @@ extern "C" int csb_launch_compress(const struct csb_compress_args *a, csb_stream
 		in_cap = CSB_FRAGMENT_MAX;
 	p.in_cap = in_cap;
 	p.in_area = ((in_cap + 15u) & ~15u) + kInPad;
-	p.group_smem = p.table_bytes + p.in_area + 16 + 8 * kTokens;
+	p.group_smem = p.table_bytes + p.in_area + 16;
 
 	const int G = a->lanes ? a->lanes : 32;
 	const int ctas_per_sm = a->ctas_per_sm > 0 ? a->ctas_per_sm : 1;
@@ -723,7 +729,7 @@ extern "C" int csb_launch_compress(const struct csb_compress_args *a, csb_stream
 	// stage, 2 = never stage.
 	bool staged = true;
 	if (G == 32 && a->stage_input != 1) {
-		const uint32_t lean = p.table_bytes + 16 + 8 * kTokens;
+		const uint32_t lean = p.table_bytes + 16;
 		const int lean_groups = (int)(budget / lean) < max_groups ? (int)(budget / lean) : max_groups;
 		// (a batch that fits the staged slots of the machine in one go gains nothing from more slots)
 		if (a->stage_input == 2 || (groups < 8 && lean_groups >= 2 * groups && a->n_blocks > (uint32_t)(di.sm_count * (groups > 0 ? groups : 1)))) {
