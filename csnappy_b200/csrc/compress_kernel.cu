@@ -385,6 +385,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) compress_kernel(const Compress
 		bool fin;
 		do {
 			fin = false;
+			if (n < kTailMargin) {  // csnappy_compress.c:497: too short to probe at all -- one literal, and no read past n
+				fin = true;
+				break;
+			}
 			// ---- fast path (G == 32): a window of CONSECUTIVE positions in which no two lanes share a hash slot ----
 			// The common window of compressible data: lanes 0..cut-1 probe wbase + lane with stride 1 (probe indices
 			// j0 + lane <= 31: page start, right behind a copy, or the stride-1 head of a later window), so
