@@ -196,6 +196,8 @@ __global__ void __launch_bounds__(kLaneThreads) decompress_lane_kernel(const Lan
 	uint32_t blk = 0, cap = 0, ip = 0, op = 0, rem = 0, mode = M_LIT, off = 0;
 	uintptr_t src = 0, src_end = 0, dst = 0;
 	uint64_t acc0 = 0, acc1 = 0, pat = 0;  // acc: bytes [op & ~15, op) of the output, not yet stored
+	uint64_t prv1 = 0;     // the 8 bytes in front of the accumulator, as this lane stored them ...
+	bool prv_ok = false;   // ... unless the warp-wide bulk copy wrote them
 	extern __shared__ __align__(128) uint8_t lane_smem[];
 	const uint32_t ring = smem_u32(lane_smem) + threadIdx.x * kRing;
 	uintptr_t have_line = 1;  // never a line address
@@ -242,6 +244,7 @@ __global__ void __launch_bounds__(kLaneThreads) decompress_lane_kernel(const Lan
 					src_end = src + ilen;
 					ip = op = rem = 0;
 					acc0 = acc1 = 0;
+					prv_ok = false;
 					mode = M_LIT;
 					if ((a.flags & 4u) && ilen == cap)
 						rem = ilen;  // stored block (block_compressor.c:378): the whole input is one literal payload
@@ -307,8 +310,18 @@ __global__ void __launch_bounds__(kLaneThreads) decompress_lane_kernel(const Lan
 				have = false;
 				rem = 0;
 			} else if (mode == M_PATTERN && rem) {
-				flush_partial(dst, cap, op, acc0, acc1);
-				pat = load16(dst + op - off, off, dst + cap).lo;
+				// the last `off` (1, 2, 4, 8) bytes of the output.  They are still in registers -- the accumulator and the
+				// vector stored before it -- so a run of pattern copies (a zero page is 64 of them) never waits for its
+				// own stores to come back from L2; only behind a bulk copy they have to be read from memory.
+				const uint32_t k = op & 15u;
+				if (k >= off || prv_ok) {
+					// 8 bytes ending at op: from (prv1, acc0) for k < 8, from (acc0, acc1) otherwise
+					const uint64_t l8 = k < 8 ? shr_pair(prv1, acc0, k) : shr_pair(acc0, acc1, k - 8u);
+					pat = l8 >> (8u * (8u - off));
+				} else {
+					flush_partial(dst, cap, op, acc0, acc1);
+					pat = load16(dst + op - off, off, dst + cap).lo;
+				}
 				if (off == 1)
 					pat = (pat & 0xffull) * 0x0101010101010101ull;
 				else if (off == 2)
@@ -338,7 +351,8 @@ __global__ void __launch_bounds__(kLaneThreads) decompress_lane_kernel(const Lan
 				ip += n_;
 				op += n_;
 				rem -= n_;
-				moved = true;  // the ring does not hold the new read position yet
+				prv_ok = false;  // other lanes wrote the bytes in front of the accumulator
+				moved = true;    // the ring does not hold the new read position yet
 			}
 		}
 		__syncwarp(full);
@@ -385,6 +399,8 @@ __global__ void __launch_bounds__(kLaneThreads) decompress_lane_kernel(const Lan
 			acc1 |= q ? t0 : t1;
 			if (k + n >= 16) {
 				stg128(dst + (op & ~15u), acc0, acc1);	// a complete vector lies below op + n <= cap
+				prv1 = acc1;
+				prv_ok = true;
 				acc0 = q ? t1 : t2;
 				acc1 = q ? t2 : 0ull;
 			}
@@ -401,6 +417,8 @@ __global__ void __launch_bounds__(kLaneThreads) decompress_lane_kernel(const Lan
 				const uintptr_t at = dst + (op & ~15u);  // the last of these vectors ends at or below op + rem <= cap
 				for (uint32_t e = 0; e < more; ++e)
 					stg128(at + 16 * e, v0, v1);
+				if (more)
+					prv1 = v1;
 				op += 16 * more;
 				rem -= 16 * more;
 			}
