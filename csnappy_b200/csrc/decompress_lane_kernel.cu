@@ -196,8 +196,8 @@ __global__ void __launch_bounds__(kLaneThreads) decompress_lane_kernel(const Lan
 	uint32_t blk = 0, cap = 0, ip = 0, op = 0, rem = 0, mode = M_LIT, off = 0;
 	uintptr_t src = 0, src_end = 0, dst = 0;
 	uint64_t acc0 = 0, acc1 = 0, pat = 0;  // acc: bytes [op & ~15, op) of the output, not yet stored
-	uint64_t prv1 = 0;     // the 8 bytes in front of the accumulator, as this lane stored them ...
-	bool prv_ok = false;   // ... unless the warp-wide bulk copy wrote them
+	uint64_t prv0 = 0, prv1 = 0;  // the 16 bytes in front of the accumulator, as this lane stored them ...
+	bool prv_ok = false;          // ... unless the warp-wide bulk copy wrote them
 	extern __shared__ __align__(128) uint8_t lane_smem[];
 	const uint32_t ring = smem_u32(lane_smem) + threadIdx.x * kRing;
 	uintptr_t have_line = 1;  // never a line address
@@ -364,17 +364,32 @@ __global__ void __launch_bounds__(kLaneThreads) decompress_lane_kernel(const Lan
 				n = 16 - (op & 15u);  // align the output for the bulk copy (16 when it already is: never here)
 			U128 v;
 			v.lo = v.hi = pat;
+			bool from_regs = false;
 			if (mode == M_NEAR) {
-				// offsets 3, 5..7, 9..30: rounds of at most `off` bytes read only what is already there; the
-				// accumulator's bytes must be in memory first
+				// offsets 3, 5..7, 9..30: rounds of at most `off` bytes read only what is already there.  The last
+				// 16 + (op & 15) bytes of the output are still in registers (the vector stored last + the accumulator):
+				// a source inside that window is cut out of them (9 % of the copies of URL text; a store followed by a
+				// load of the same bytes is a round trip through L2 that the whole warp waits for); a source further
+				// back, or behind a bulk copy, needs the accumulator's bytes in memory first.
 				if (n > off)
 					n = off;
-				flush_partial(dst, cap, op, acc0, acc1);
+				const uint32_t k = op & 15u;
+				from_regs = off <= k || (prv_ok && off <= 16u + k);
+				if (from_regs) {
+					const uint32_t b = 16u + k - off, w = b >> 3, sft = b & 7u;  // byte offset into prv0 prv1 acc0 acc1
+					const uint64_t x0 = w == 0 ? prv0 : (w == 1 ? prv1 : (w == 2 ? acc0 : acc1));
+					const uint64_t x1 = w == 0 ? prv1 : (w == 1 ? acc0 : (w == 2 ? acc1 : 0ull));
+					const uint64_t x2 = w == 0 ? acc0 : (w == 1 ? acc1 : 0ull);
+					v.lo = shr_pair(x0, x1, sft);
+					v.hi = shr_pair(x1, x2, sft);
+				} else {
+					flush_partial(dst, cap, op, acc0, acc1);
+				}
 			}
 			if (mode == M_LIT) {
 				v = ring_load16(ring, src + ip, n);
 				ip += n;
-			} else if (mode != M_PATTERN) {
+			} else if (mode != M_PATTERN && !from_regs) {
 				v = load16(dst + op - off, n, dst + cap);
 			}
 			// append the n low bytes of v (op + n <= cap was checked with the tag)
@@ -399,6 +414,7 @@ __global__ void __launch_bounds__(kLaneThreads) decompress_lane_kernel(const Lan
 			acc1 |= q ? t0 : t1;
 			if (k + n >= 16) {
 				stg128(dst + (op & ~15u), acc0, acc1);	// a complete vector lies below op + n <= cap
+				prv0 = acc0;
 				prv1 = acc1;
 				prv_ok = true;
 				acc0 = q ? t1 : t2;
@@ -417,8 +433,10 @@ __global__ void __launch_bounds__(kLaneThreads) decompress_lane_kernel(const Lan
 				const uintptr_t at = dst + (op & ~15u);  // the last of these vectors ends at or below op + rem <= cap
 				for (uint32_t e = 0; e < more; ++e)
 					stg128(at + 16 * e, v0, v1);
-				if (more)
+				if (more) {
+					prv0 = v0;
 					prv1 = v1;
+				}
 				op += 16 * more;
 				rem -= 16 * more;
 			}
