@@ -17,9 +17,11 @@ with no data-path collective ("weak": per-GPU batch fixed); NCCL is used for the
 the max-over-ranks only.
 
 `value`      device-resident: inputs already in HBM, CUDA events around K steps.
-`e2e`        same metric through the host-buffer C-ABI (csnappy_batch_*_host) with pinned
-             host buffers: H2D of every page and D2H of every result inside the timed region.
-`e2e_pageable` the same calls on ordinary (pageable) caller memory.
+`e2e`        same metric through the host-buffer C-ABI (csnappy_bc_compress_host + csnappy_bc_decompress_host, the
+             block_compressor page container) with pinned host buffers: H2D of every page and D2H of every
+             result inside the timed region.
+`e2e_concurrent` (N = 1) the two calls running in two threads at once (both PCIe directions busy).
+`e2e_pageable`   (N = 1) the same calls on ordinary (pageable) caller memory.
 `roofline`   dominant kernel (compress) against the measured HBM copy peak;
              algorithmic bytes = sum N_in + sum C_out + 4 B.
 `workloads`  BASELINE.json configs[2] and [3], device-resident, every rank, reduced like `value`:
