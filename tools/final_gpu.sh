@@ -1,4 +1,4 @@
-O=gpurun_out/r02G; mkdir -p $O
+O=gpurun_out/r02H; mkdir -p $O
 timeout 120 python __graft_entry__.py smoke > $O/smoke.txt 2>&1; tail -1 $O/smoke.txt
 timeout 900 python -m pytest tests -m gpu -x -q > $O/pytest.txt 2>&1; tail -2 $O/pytest.txt
 python bench.py > $O/bench.json 2> $O/bench.err; tail -3 $O/bench.err
@@ -10,3 +10,4 @@ ncu --set full --import-source on --clock-control none -k regex:^compress_kernel
 for t in memcheck synccheck racecheck; do timeout 500 compute-sanitizer --tool $t python tools/sanitize_run.py > $O/sanitizer_$t.log 2>&1; echo "$t rc=$?"; tail -1 $O/sanitizer_$t.log; done
 python -c "import json; d=json.load(open('$O/bench.json')); print(d['value'], d['compress_gbs'], d['decompress_gbs'], d['e2e']['value'], d['e2e_concurrent']['value'], d['e2e_pageable']['value'], d['roofline']['frac'])"
 ls $O
+timeout 400 python tools/fuzz_gpu.py 300 2>&1 | tail -1 | tee $O/fuzz_soak.txt
