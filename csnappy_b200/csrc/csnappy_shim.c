@@ -65,7 +65,7 @@ int csnappy_b200_device_ok(void) { return csnappy_b200_device_count() > 0; }
 uint64_t csnappy_b200_kernel_launches(void) { return csb_launch_count(); }
 
 /* ---- tuning knobs ------------------------------------------------------- */
-static int g_compress_lanes, g_decompress_lanes, g_ctas_per_sm, g_stage_input, g_smem_kb, g_host_register, g_stream_min, g_lane_warps, g_copy_threads, g_no_bounce, g_compress_stage;
+static int g_compress_lanes, g_decompress_lanes, g_ctas_per_sm, g_stage_input, g_smem_kb, g_host_register, g_stream_min, g_lane_warps, g_copy_threads, g_no_bounce, g_compress_stage, g_chunk_mb;
 
 int csnappy_b200_set_tuning(const char *key, int value)
 {
@@ -102,6 +102,12 @@ int csnappy_b200_set_tuning(const char *key, int value)
 		if (value < 0 || value > 64)
 			return CSNAPPY_E_BAD_ARG;
 		g_lane_warps = value;
+		return 0;
+	}
+	if (!strcmp(key, "chunk_mb")) { /* MiB per chunk of the host-buffer pipelines (0 = default 32) */
+		if (value < 0 || value > 1024)
+			return CSNAPPY_E_BAD_ARG;
+		g_chunk_mb = value;
 		return 0;
 	}
 	if (!strcmp(key, "copy_threads")) { /* helper threads staging pageable caller memory (0 = default; read when the pool starts) */
@@ -985,7 +991,7 @@ static int run_cjob(struct cjob *j)
 static uint32_t chunk_units(uint32_t unit_bytes, uint64_t n_units, int G)
 {
 	/* ~32 MiB per chunk keeps PCIe busy and the kernels full; small inputs are still cut into a few chunks per device */
-	uint64_t units = (32ull << 20) / unit_bytes, per_dev = (n_units + (uint64_t)G - 1) / (uint64_t)G;
+	uint64_t units = ((uint64_t)(g_chunk_mb > 0 ? g_chunk_mb : 32) << 20) / unit_bytes, per_dev = (n_units + (uint64_t)G - 1) / (uint64_t)G;
 	if (units > (per_dev + 3) / 4)
 		units = (per_dev + 3) / 4;
 	if (units < 256)
@@ -1240,7 +1246,7 @@ static size_t pick_chunk_blocks(uint64_t in_stride, uint64_t out_stride, uint32_
 {
 	/* ~32 MiB of the larger side per chunk keeps PCIe busy and the kernels full */
 	uint64_t per = in_stride > out_stride ? in_stride : out_stride;
-	uint64_t blocks = per ? (32ull << 20) / per : n_blocks;
+	uint64_t blocks = per ? ((uint64_t)(g_chunk_mb > 0 ? g_chunk_mb : 32) << 20) / per : n_blocks;
 	if (blocks < 1024)
 		blocks = 1024;
 	if (blocks > n_blocks)

@@ -201,6 +201,7 @@ uint64_t csnappy_b200_kernel_launches(void); /* kernels launched by this library
  *   "stream_decode_min"       bytes from which ONE single stream takes the parallel stream decoder; -1: never
  *   "copy_threads"            helper threads that stage PAGEABLE caller memory through pinned buffers in the
  *                             host-buffer pipelines (read when the pool starts; default 7 on >= 16 cores)
+ *   "chunk_mb"                MiB per chunk of the host-buffer pipelines (default 32; measured flat from 32 to 128)
  *   "no_bounce"               1: hand pageable caller memory straight to cudaMemcpyAsync (round-1 behaviour)
  *   "host_register"           1: page-lock the caller's buffers for the duration of a host-buffer call (measured
  *                             slower than the staging above unless the same buffers are registered once by the caller) */

@@ -10,6 +10,9 @@ import csnappy_b200 as cs
 from csnappy_b200 import synth
 
 PAGE = 4096
+import os
+if os.environ.get("CHUNK_MB"):
+    cs.set_tuning("chunk_mb", int(os.environ["CHUNK_MB"]))
 for B in [int(x) for x in (sys.argv[1:] or ["262144", "524288", "1048576"])]:
     pages = synth.mixed_pages(B, PAGE, seed=0x5EED0001, device="cuda")
     h_in = torch.empty(B * PAGE, dtype=torch.uint8, pin_memory=True)
