@@ -232,3 +232,17 @@ def test_bulk_harness_port_vs_reference():
     d2, n2, s2, _ = oracle.batch_decompress(o2, l2, 4096, "reference", threads=1)
     assert (s1 == 0).all() and (s2 == 0).all() and (n1 == 4096).all() and (n2 == 4096).all()
     assert (d1[:, :4096] == pages).all() and (d2[:, :4096] == pages).all()
+
+
+def test_batch_runner_is_the_bench_cpu_protocol():
+    """oracle.BatchRunner (bench.py's one CPU-baseline protocol): buffers allocated once, compress + decompress timed in
+    the C harness, exact round trip, and the same bytes as the single-block entry points."""
+    pages = fuzz_pages(31, 200, 4096)
+    units = np.frombuffer(b"".join(pages), dtype=np.uint8).reshape(len(pages), 4096)
+    for impl in (["reference"] if oracle.have_reference() else []) + ["port"]:
+        r = oracle.BatchRunner(units, 13, impl, threads=3)
+        tc, td = r.measure(warmup=1, steps=2)
+        assert tc > 0 and td > 0
+        chk = oracle.reference() if impl == "reference" else oracle.port()
+        for i in (0, 57, 199):
+            assert r.compressed(i) == chk.compress_fragment(pages[i], 13)
