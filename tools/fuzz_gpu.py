@@ -2,7 +2,7 @@
 """Long randomized parity run on the GPU box: many seeds / block sizes / table sizes / lane groups,
 compressed bytes and decoder results compared with the unmodified reference (oracle/_ref).
 
-    python tools/fuzz_gpu.py [seconds]
+    python tools/fuzz_gpu.py [seconds] [seed]
 """
 import sys
 import time
@@ -17,8 +17,9 @@ import oracle
 from cases import fuzz_pages
 
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
+seed = int(sys.argv[2]) if len(sys.argv) > 2 else 20261017
 chk = oracle.best()
-rng = np.random.default_rng(20261017)
+rng = np.random.default_rng(seed)
 t0 = time.time()
 rounds = blocks = streams = 0
 while time.time() - t0 < budget:
