@@ -447,6 +447,40 @@ def test_host_paths_pinned_and_pageable_agree(cs, chk, bounce):
         cs.set_tuning("no_bounce", 0)
 
 
+def test_packed_offsets_beyond_4_gib(cs, chk):
+    """1.25 Mi mixed pages with every 5th page random: slots 5.6 GiB, PACKED payload > 4 GiB, so the u64 offsets that
+    csnappy_batch_pack scans and csnappy_batch_decompress follows (in_off) cross 2^32; exact round trip + the tail pages
+    (the ones whose offsets are beyond 2^32) byte-identical to the CPU reference."""
+    from csnappy_b200 import synth
+
+    B = 1310720
+    d_pages = synth.mixed_pages(B, 4096, seed=0x5EED0004, device="cuda", text="urls").view(B, 4096)
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(5)
+    d_pages[::5] = torch.randint(0, 256, (len(range(0, B, 5)), 4096), dtype=torch.uint8, device="cuda", generator=gen)
+    d_pages[1::5] = torch.randint(0, 256, (len(range(1, B, 5)), 4096), dtype=torch.uint8, device="cuda", generator=gen)
+    d_pages[2::5] = torch.randint(0, 256, (len(range(2, B, 5)), 4096), dtype=torch.uint8, device="cuda", generator=gen)
+    flat = d_pages.view(-1)
+    ostride = cs.api.out_stride_for(4096)
+    out, out_len = cs.batch_compress_fragments(flat, 4096, B, 13)
+    packed, off = cs.batch_pack(out, ostride, out_len, B)
+    total = int(off[-1])
+    assert total > (1 << 32), total
+    assert int(off[-1]) == int(out_len.to(torch.int64).sum())
+    del out
+    back, back_len, status = cs.batch_decompress(packed, out_len, B, 4096, in_off=off[:-1].contiguous())
+    torch.cuda.synchronize()
+    assert int((status != 0).sum()) == 0 and int((back_len != 4096).sum()) == 0
+    assert torch.equal(back.view(B, 4096), d_pages)
+    # the last pages live beyond 2^32 in the packed payload
+    h_off = off[-65:].cpu().numpy()
+    assert h_off[0] > (1 << 32)
+    tail = packed[int(h_off[0]): int(h_off[-1])].cpu().numpy().tobytes()
+    host = d_pages[B - 64:].cpu().numpy()
+    exp = b"".join(chk.compress_fragment(host[i].tobytes(), 13) for i in range(64))
+    assert tail == exp
+
+
 def test_lane_decoder_blocks_after_failed_blocks_in_the_same_lane(cs, chk, urls):
     """Lane-per-block decoder with few lanes (one warp per SM), so every lane decodes ~10 blocks one after the other:
     a block that fails half-way leaves a line of its input in flight towards the lane's shared-memory ring; the next
